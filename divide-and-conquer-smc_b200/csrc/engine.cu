@@ -1,0 +1,1028 @@
+// engine.cu — host runtime of the DC-SMC node engine + the C ABI of include/dcsmc.h.
+//
+// Replaces, for the hot path only, the reference's L3/L4 machinery
+// (dc/DistributedDC.java, dc/DCRecursionTask.java): instead of one Hazelcast task per node the
+// tree is cut into level batches ("steps"); every step is a fixed sequence of kernel launches
+// over all its sibling nodes. A static memory plan decides which populations are resident
+// when; child populations are released as soon as their parent has consumed them
+// (DCRecursionTask.java:113).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dcsmc.h"
+#include "kernels.cuh"
+
+using namespace dcsmc;
+
+namespace {
+
+thread_local std::string g_createError;
+
+struct Step {
+  int offset = 0;  // into stepNodes
+  int count = 0;
+  bool leaf = false;
+  std::vector<int> releaseAfter;  // nodes whose slots are returned after this step
+};
+
+struct Slot {
+  size_t offset = 0;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct dcsmc_engine {
+  dcsmc_options opt{};
+  mutable std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // topology / model (host)
+  int nNodes = 0, root = 0;
+  std::vector<int32_t> childOffsets, children, parent, height, javaHash;
+  int model = -1;
+  std::vector<int32_t> leafKind, nTrials, nSuccesses;
+  std::vector<double> leafObs;
+  double rate = 1.0;
+  int nStates = 0;
+  std::vector<double> markovT, markovPrior;
+  std::vector<std::vector<double>> injHost;  // kept only until uploaded
+  std::vector<double*> injDev;
+
+  // device tables
+  NodeDev* dNodes = nullptr;
+  NodeStats* dStats = nullptr;
+  LeafConst* dLeaf = nullptr;
+  int32_t* dChildren = nullptr;
+  int32_t* dStepNodes = nullptr;
+  size_t stepNodesCap = 0;
+  double** dInj = nullptr;
+  uint64_t* dJavaState = nullptr;
+  double *dMarkovT = nullptr, *dMarkovPrior = nullptr;
+  bool tablesDirty = true;
+
+  // population pool
+  char* pool = nullptr;
+  size_t poolBytes = 0;
+  std::multimap<size_t, size_t> freeBySize;  // bytes -> offset (exact-size free lists)
+  size_t poolTop = 0;
+  std::vector<Slot> slot;        // per node
+  std::vector<char> resident;    // per node
+  std::vector<NodeDev> hNodes;   // host mirror
+  std::vector<dcsmc_node_stats_t> hStats;
+  int Npad = 0;
+
+  // scratch
+  double* dCdf = nullptr;
+  size_t cdfCap = 0;
+  unsigned long long* dDesc = nullptr;  // descA | descB | ticket
+  size_t descCap = 0;
+
+  // measurement
+  dcsmc_run_info info{};
+  bool profile = false;
+  double profMs[DCSMC_K_COUNT] = {0};
+  int64_t profLaunches[DCSMC_K_COUNT] = {0};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> profEvents;
+
+  int fail(int code, const char* fmt, ...) const {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return e->fail(DCSMC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),     \
+                     __FILE__, __LINE__);                                                     \
+  } while (0)
+
+namespace {
+
+int nChildrenOf(const dcsmc_engine* e, int n) { return e->childOffsets[n + 1] - e->childOffsets[n]; }
+
+int nodeKind(const dcsmc_engine* e, int n) {
+  if (nChildrenOf(e, n) > 0) return KIND_INTERNAL;
+  if (e->model == DCSMC_MODEL_MARKOV) return KIND_LEAF_GAUSS;  // no proposal draws
+  if (!e->leafKind.empty() && e->leafKind[n] == DCSMC_LEAF_GAUSS_OBS) return KIND_LEAF_GAUSS;
+  return KIND_LEAF_BINOMIAL;
+}
+
+int slotsPerParticle(const dcsmc_engine* e, int n) {
+  const int k = nodeKind(e, n);
+  if (k == KIND_INTERNAL) return 1;
+  if (k == KIND_LEAF_BINOMIAL) return 2 * e->opt.maxBetaAttempts;
+  return 0;
+}
+
+size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bytes of one node's resident population
+size_t slotBytes(const dcsmc_engine* e, int n) {
+  const size_t NP = (size_t)e->Npad;
+  size_t b = 0;
+  if (e->model == DCSMC_MODEL_MARKOV) {
+    b = NP * 4 /*istate*/ + NP * 8 /*logw*/ + NP * 4 /*anc*/;
+  } else {
+    const int cols = nodeKind(e, n) == KIND_INTERNAL ? 6 : 2;
+    b = NP * 8 * cols + NP * 8 /*logw*/ + NP * 4 /*anc*/;
+  }
+  return alignUp(b, 256);
+}
+
+bool poolAlloc(dcsmc_engine* e, int n) {
+  const size_t b = slotBytes(e, n);
+  auto it = e->freeBySize.find(b);
+  size_t off;
+  if (it != e->freeBySize.end()) {
+    off = it->second;
+    e->freeBySize.erase(it);
+  } else {
+    if (e->poolTop + b > e->poolBytes) return false;
+    off = e->poolTop;
+    e->poolTop += b;
+  }
+  e->slot[n] = Slot{off, b};
+  e->resident[n] = 1;
+  return true;
+}
+
+void poolFree(dcsmc_engine* e, int n) {
+  if (!e->resident[n]) return;
+  e->freeBySize.emplace(e->slot[n].bytes, e->slot[n].offset);
+  e->resident[n] = 0;
+}
+
+void fillNodeDev(dcsmc_engine* e, int n) {
+  NodeDev& d = e->hNodes[n];
+  const size_t NP = (size_t)e->Npad;
+  char* base = e->pool + e->slot[n].offset;
+  d.childBegin = e->childOffsets[n];
+  d.nChildren = nChildrenOf(e, n);
+  d.kind = nodeKind(e, n);
+  d.pad = 0;
+  if (e->model == DCSMC_MODEL_MARKOV) {
+    d.state = nullptr;
+    d.logw = reinterpret_cast<double*>(base);
+    d.istate = reinterpret_cast<int32_t*>(base + NP * 8);
+    d.anc = reinterpret_cast<int32_t*>(base + NP * 12);
+  } else {
+    const int cols = d.kind == KIND_INTERNAL ? 6 : 2;
+    d.state = reinterpret_cast<double*>(base);
+    d.logw = reinterpret_cast<double*>(base + NP * 8 * cols);
+    d.anc = reinterpret_cast<int32_t*>(base + NP * 8 * (cols + 1));
+    d.istate = nullptr;
+  }
+}
+
+void leafConstFor(const dcsmc_engine* e, int node, LeafConst& lc) {
+  memset(&lc, 0, sizeof lc);
+  if (nodeKind(e, node) == KIND_LEAF_GAUSS) {
+    lc.obs = e->leafObs.empty() ? 0.0 : e->leafObs[node];
+    return;
+  }
+  if (nodeKind(e, node) != KIND_LEAF_BINOMIAL) return;
+  // MultiLevelProposalFactory.build (MultiLevelProposalFactory.java:40-49): Beta(1+s, 1+(n-s)),
+  // then the constants of Cheng's BB/BC samplers (commons-math3 BetaDistribution.sample()).
+  const int32_t n = e->nTrials[node], s = e->nSuccesses[node];
+  const double shapeA = 1 + s, shapeB = 1 + (n - s);
+  lc.n = n;
+  lc.s = s;
+  lc.a0 = shapeA;
+  const double mn = std::fmin(shapeA, shapeB), mx = std::fmax(shapeA, shapeB);
+  lc.useBB = mn > 1;
+  if (lc.useBB) {
+    lc.a = mn;
+    lc.b = mx;
+    lc.alpha = lc.a + lc.b;
+    lc.beta = std::sqrt((lc.alpha - 2.) / (2. * lc.a * lc.b - lc.alpha));
+    lc.gamma = lc.a + 1. / lc.beta;
+  } else {
+    lc.a = mx;
+    lc.b = mn;
+    lc.alpha = lc.a + lc.b;
+    lc.beta = 1. / lc.b;
+    lc.delta = 1. + lc.a - lc.b;
+    lc.k1 = lc.delta * (0.0138889 + 0.0416667 * lc.b) / (lc.a * lc.beta - 0.777778);
+    lc.k2 = 0.25 + (0.5 + 0.25 / lc.delta) * lc.b;
+  }
+  lc.logAlpha = dc_log(lc.alpha);
+  // SpecialFunctions.logBinomial(n, s): per-node constant, hoisted out of the particle loop
+  lc.logBinom = std::lgamma((double)n + 1.0) - std::lgamma((double)s + 1.0) - std::lgamma((double)(n - s) + 1.0);
+}
+
+int ensureDevice(dcsmc_engine* e) {
+  CK(cudaSetDevice(e->opt.device));
+  return DCSMC_OK;
+}
+
+// (re)build the device-side tables that do not depend on the memory plan
+int uploadTables(dcsmc_engine* e) {
+  if (!e->tablesDirty) return DCSMC_OK;
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
+  if (e->model < 0) return e->fail(DCSMC_ESTATE, "no proposal model set (dcsmc_set_*_model)");
+  const int nN = e->nNodes;
+  auto re = [&](void** p, size_t bytes) -> cudaError_t {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc(p, bytes ? bytes : 8);
+  };
+  CK(re((void**)&e->dNodes, sizeof(NodeDev) * nN));
+  CK(re((void**)&e->dStats, sizeof(NodeStats) * nN));
+  CK(re((void**)&e->dLeaf, sizeof(LeafConst) * nN));
+  CK(re((void**)&e->dChildren, sizeof(int32_t) * std::max<size_t>(1, e->children.size())));
+  CK(re((void**)&e->dInj, sizeof(double*) * nN));
+  CK(re((void**)&e->dJavaState, sizeof(uint64_t) * nN));
+  CK(cudaMemcpyAsync(e->dChildren, e->children.data(), sizeof(int32_t) * e->children.size(),
+                     cudaMemcpyHostToDevice, e->stream));
+  std::vector<LeafConst> lc(nN);
+  if (e->model == DCSMC_MODEL_MULTILEVEL)
+    for (int n = 0; n < nN; ++n) leafConstFor(e, n, lc[n]);
+  else
+    memset(lc.data(), 0, sizeof(LeafConst) * nN);
+  CK(cudaMemcpyAsync(e->dLeaf, lc.data(), sizeof(LeafConst) * nN, cudaMemcpyHostToDevice, e->stream));
+  std::vector<uint64_t> js(nN, 0);
+  for (int n = 0; n < nN; ++n)
+    js[n] = java_scramble(java_node_seed(e->opt.masterRandomSeed, e->javaHash.empty() ? 0 : e->javaHash[n]));
+  CK(cudaMemcpyAsync(e->dJavaState, js.data(), sizeof(uint64_t) * nN, cudaMemcpyHostToDevice, e->stream));
+  if (e->model == DCSMC_MODEL_MARKOV) {
+    CK(re((void**)&e->dMarkovT, sizeof(double) * e->markovT.size()));
+    CK(re((void**)&e->dMarkovPrior, sizeof(double) * e->markovPrior.size()));
+    CK(cudaMemcpyAsync(e->dMarkovT, e->markovT.data(), sizeof(double) * e->markovT.size(),
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->dMarkovPrior, e->markovPrior.data(), sizeof(double) * e->markovPrior.size(),
+                       cudaMemcpyHostToDevice, e->stream));
+  }
+  CK(cudaMemsetAsync(e->dStats, 0, sizeof(NodeStats) * nN, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->hNodes.assign(nN, NodeDev{});
+  e->hStats.assign(nN, dcsmc_node_stats_t{});
+  e->slot.assign(nN, Slot{});
+  e->resident.assign(nN, 0);
+  e->freeBySize.clear();
+  e->poolTop = 0;
+  e->tablesDirty = false;
+  return DCSMC_OK;
+}
+
+int uploadInjected(dcsmc_engine* e) {
+  if (e->opt.rngMode != DCSMC_RNG_INJECTED) return DCSMC_OK;
+  if ((int)e->injDev.size() != e->nNodes) e->injDev.assign(e->nNodes, nullptr);
+  for (int n = 0; n < e->nNodes; ++n) {
+    if (n < (int)e->injHost.size() && !e->injHost[n].empty()) {
+      if (e->injDev[n]) cudaFree(e->injDev[n]);
+      CK(cudaMalloc((void**)&e->injDev[n], sizeof(double) * e->injHost[n].size()));
+      CK(cudaMemcpyAsync(e->injDev[n], e->injHost[n].data(), sizeof(double) * e->injHost[n].size(),
+                         cudaMemcpyHostToDevice, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      e->injHost[n].clear();
+      e->injHost[n].shrink_to_fit();
+    }
+  }
+  CK(cudaMemcpyAsync(e->dInj, e->injDev.data(), sizeof(double*) * e->nNodes, cudaMemcpyHostToDevice, e->stream));
+  return DCSMC_OK;
+}
+
+int ensurePool(dcsmc_engine* e) {
+  if (e->pool) return DCSMC_OK;
+  size_t freeB = 0, totalB = 0;
+  CK(cudaMemGetInfo(&freeB, &totalB));
+  size_t budget = e->opt.memoryBudgetBytes > 0 ? (size_t)e->opt.memoryBudgetBytes : (size_t)(freeB * 0.85);
+  // the pool never needs more than "everything resident at once"
+  size_t all = 0;
+  for (int n = 0; n < e->nNodes; ++n) all += slotBytes(e, n);
+  // scratch for the largest conceivable step is taken from the same budget (cdf: 8 B/particle)
+  e->poolBytes = std::min(budget, all);
+  CK(cudaMalloc((void**)&e->pool, e->poolBytes));
+  return DCSMC_OK;
+}
+
+// ---- planning --------------------------------------------------------------------------------
+
+struct Plan {
+  std::vector<Step> steps;
+  std::vector<int32_t> stepNodes;
+};
+
+void collectSubtree(const dcsmc_engine* e, int r, std::vector<int>& out) {
+  std::vector<int> stack{r};
+  while (!stack.empty()) {
+    const int n = stack.back();
+    stack.pop_back();
+    if (e->resident[n] && n != r) continue;  // already computed (e.g. unpacked) — treat as done
+    out.push_back(n);
+    for (int c = e->childOffsets[n]; c < e->childOffsets[n + 1]; ++c)
+      if (!e->resident[e->children[c]]) stack.push_back(e->children[c]);
+  }
+}
+
+// Emit level batches for the union of the subtrees under `roots`; allocates slots as it goes.
+// Returns false (and rolls nothing back) if the pool overflows.
+bool emitLevels(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan, bool dryRun,
+                size_t& peakTop) {
+  std::vector<int> nodes;
+  for (int r : roots) collectSubtree(e, r, nodes);
+  std::map<int, std::vector<int>> byHeight;
+  for (int n : nodes) byHeight[e->height[n]].push_back(n);
+  for (auto& kv : byHeight) {
+    std::vector<int>& lvl = kv.second;
+    std::sort(lvl.begin(), lvl.end());
+    Step st;
+    st.leaf = kv.first == 0;
+    st.offset = (int)plan.stepNodes.size();
+    st.count = (int)lvl.size();
+    for (int n : lvl) {
+      if (!poolAlloc(e, n)) return false;
+      peakTop = std::max(peakTop, e->poolTop);
+      plan.stepNodes.push_back(n);
+    }
+    if (!e->opt.retainPopulations)
+      for (int n : lvl)
+        for (int c = e->childOffsets[n]; c < e->childOffsets[n + 1]; ++c) {
+          st.releaseAfter.push_back(e->children[c]);
+          poolFree(e, e->children[c]);
+        }
+    plan.steps.push_back(std::move(st));
+  }
+  (void)dryRun;
+  return true;
+}
+
+struct PoolState {
+  std::multimap<size_t, size_t> freeBySize;
+  size_t poolTop;
+  std::vector<Slot> slot;
+  std::vector<char> resident;
+};
+PoolState savePool(const dcsmc_engine* e) { return PoolState{e->freeBySize, e->poolTop, e->slot, e->resident}; }
+void restorePool(dcsmc_engine* e, const PoolState& s) {
+  e->freeBySize = s.freeBySize;
+  e->poolTop = s.poolTop;
+  e->slot = s.slot;
+  e->resident = s.resident;
+}
+
+// Memory-aware recursive planner: try the whole root set level by level; if the pool
+// overflows, halve the root set, or descend below a single root.
+int planRoots(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan) {
+  if (roots.empty()) return DCSMC_OK;
+  {
+    const PoolState saved = savePool(e);
+    Plan trial;
+    trial.stepNodes = plan.stepNodes;
+    size_t peak = 0;
+    if (emitLevels(e, roots, trial, false, peak)) {
+      for (auto& s : trial.steps) plan.steps.push_back(std::move(s));
+      plan.stepNodes = std::move(trial.stepNodes);
+      return DCSMC_OK;
+    }
+    restorePool(e, saved);
+  }
+  if (roots.size() > 1) {
+    const size_t half = roots.size() / 2;
+    std::vector<int> a(roots.begin(), roots.begin() + half), b(roots.begin() + half, roots.end());
+    int rc = planRoots(e, a, plan);
+    if (rc) return rc;
+    return planRoots(e, b, plan);
+  }
+  const int r = roots[0];
+  if (nChildrenOf(e, r) == 0)
+    return e->fail(DCSMC_ENOMEM, "population pool (%zu bytes) cannot hold node %d", e->poolBytes, r);
+  std::vector<int> kids;
+  for (int c = e->childOffsets[r]; c < e->childOffsets[r + 1]; ++c)
+    if (!e->resident[e->children[c]]) kids.push_back(e->children[c]);
+  int rc = planRoots(e, kids, plan);
+  if (rc) return rc;
+  // all children resident now: the root alone
+  Step st;
+  st.leaf = false;
+  st.offset = (int)plan.stepNodes.size();
+  st.count = 1;
+  if (!poolAlloc(e, r))
+    return e->fail(DCSMC_ENOMEM, "population pool (%zu bytes) too small for node %d and its children",
+                   e->poolBytes, r);
+  plan.stepNodes.push_back(r);
+  if (!e->opt.retainPopulations)
+    for (int c = e->childOffsets[r]; c < e->childOffsets[r + 1]; ++c) {
+      st.releaseAfter.push_back(e->children[c]);
+      poolFree(e, e->children[c]);
+    }
+  plan.steps.push_back(std::move(st));
+  return DCSMC_OK;
+}
+
+// ---- execution -------------------------------------------------------------------------------
+
+struct ProfScope {
+  dcsmc_engine* e;
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(dcsmc_engine* e_, int cls_) : e(e_), cls(cls_) {
+    e->info.kernelLaunches++;
+    if (e->profile) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, e->stream);
+    }
+  }
+  ~ProfScope() {
+    if (e->profile) {
+      cudaEventRecord(b, e->stream);
+      e->profEvents.push_back({cls, {a, b}});
+    }
+  }
+};
+
+template <int RNG>
+int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
+  RunCtx c = base;
+  c.stepNodes = e->dStepNodes + st.offset;
+  c.nStepNodes = st.count;
+  const int N = c.N;
+  const int tilesP = (N + PROPOSE_THREADS - 1) / PROPOSE_THREADS;
+  const int tilesS = (N + SCAN_TILE - 1) / SCAN_TILE;
+  const int tilesR = (N + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
+  const long long gridP = (long long)st.count * tilesP;
+  if (gridP > 0x7fffffffLL) return e->fail(DCSMC_EINVAL, "step too large for one launch");
+  // scratch
+  const size_t needDesc = (size_t)st.count * tilesS;
+  c.descA = e->dDesc;
+  c.descB = e->dDesc + needDesc;
+  c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + 2 * needDesc);
+  CK(cudaMemsetAsync(e->dDesc, 0, (2 * needDesc + 1) * sizeof(unsigned long long), e->stream));
+
+  if (e->model == DCSMC_MODEL_MARKOV) {
+    ProfScope p(e, DCSMC_K_MARKOV);
+    k_markov_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
+  } else if (st.leaf) {
+    ProfScope p(e, DCSMC_K_LEAF);
+    k_leaf_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
+  } else {
+    ProfScope p(e, DCSMC_K_INTERNAL);
+    k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
+  }
+  {
+    ProfScope p(e, DCSMC_K_SCAN);
+    k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, e->stream>>>(c, tilesS);
+  }
+  {
+    ProfScope p(e, DCSMC_K_FINALIZE);
+    k_finalize<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
+  }
+  if (e->opt.resamplingScheme == DCSMC_STRATIFIED) {
+    ProfScope p(e, DCSMC_K_RESAMPLE);
+    k_resample_stratified<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+  } else {
+    return e->fail(DCSMC_EINVAL, "MULTINOMIAL resampling is not implemented yet");
+  }
+  CK(cudaGetLastError());
+  return DCSMC_OK;
+}
+
+int makeCtx(dcsmc_engine* e, RunCtx& c) {
+  memset(&c, 0, sizeof c);
+  const int N = e->opt.nParticles;
+  c.nodes = e->dNodes;
+  c.stats = e->dStats;
+  c.leaf = e->dLeaf;
+  c.children = e->dChildren;
+  c.N = N;
+  c.Npad = e->Npad;
+  c.scheme = e->opt.resamplingScheme;
+  c.maxAtt = e->opt.maxBetaAttempts;
+  c.nStates = e->nStates;
+  c.javaStepsInternal = e->model == DCSMC_MODEL_MARKOV ? 1 : 2;
+  c.seed = (uint64_t)e->opt.masterRandomSeed;
+  c.inj = e->dInj;
+  c.javaState = e->dJavaState;
+  c.markovT = e->dMarkovT;
+  c.markovPrior = e->dMarkovPrior;
+  c.rate = e->rate;
+  c.logRate = dc_log(e->rate);
+  c.invN = 1.0 / (double)N;
+  c.logN = dc_log((double)N);
+  c.dN = (double)N;
+  c.threshold = e->opt.relativeEssThreshold;
+  c.cdf = e->dCdf;
+  return DCSMC_OK;
+}
+
+int validateForRun(dcsmc_engine* e) {
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
+  if (e->model < 0) return e->fail(DCSMC_ESTATE, "no proposal model set (dcsmc_set_*_model)");
+  if (e->opt.rngMode == DCSMC_RNG_JAVA) {
+    if (e->javaHash.empty()) return e->fail(DCSMC_ESTATE, "DCSMC_RNG_JAVA needs dcsmc_set_node_seeds");
+    if (e->model == DCSMC_MODEL_MULTILEVEL)
+      for (int n = 0; n < e->nNodes; ++n)
+        if (nodeKind(e, n) == KIND_LEAF_BINOMIAL)
+          return e->fail(DCSMC_EINVAL,
+                         "DCSMC_RNG_JAVA cannot reproduce the variable-length Beta rejection stream of "
+                         "binomial leaves (node %d)", n);
+    if (e->model == DCSMC_MODEL_MARKOV && (e->nStates & (e->nStates - 1)) != 0)
+      return e->fail(DCSMC_EINVAL, "DCSMC_RNG_JAVA needs a power-of-two nStates (Random.nextInt rejection loop)");
+  }
+  return DCSMC_OK;
+}
+
+// run a plan: upload step lists, execute, fetch stats
+int executePlan(dcsmc_engine* e, Plan& plan) {
+  int rc;
+  const int N = e->opt.nParticles;
+  // scratch sizing
+  size_t maxStep = 0;
+  for (auto& s : plan.steps) maxStep = std::max<size_t>(maxStep, s.count);
+  const size_t tilesS = (N + SCAN_TILE - 1) / SCAN_TILE;
+  const size_t needCdf = maxStep * (size_t)e->Npad;
+  if (needCdf > e->cdfCap) {
+    if (e->dCdf) cudaFree(e->dCdf);
+    e->dCdf = nullptr;
+    CK(cudaMalloc((void**)&e->dCdf, needCdf * sizeof(double)));
+    e->cdfCap = needCdf;
+  }
+  const size_t needDesc = 2 * maxStep * tilesS + 1;
+  if (needDesc > e->descCap) {
+    if (e->dDesc) cudaFree(e->dDesc);
+    e->dDesc = nullptr;
+    CK(cudaMalloc((void**)&e->dDesc, needDesc * sizeof(unsigned long long)));
+    e->descCap = needDesc;
+  }
+  if (plan.stepNodes.size() > e->stepNodesCap) {
+    if (e->dStepNodes) cudaFree(e->dStepNodes);
+    e->dStepNodes = nullptr;
+    CK(cudaMalloc((void**)&e->dStepNodes, plan.stepNodes.size() * sizeof(int32_t)));
+    e->stepNodesCap = plan.stepNodes.size();
+  }
+  CK(cudaMemcpyAsync(e->dStepNodes, plan.stepNodes.data(), plan.stepNodes.size() * sizeof(int32_t),
+                     cudaMemcpyHostToDevice, e->stream));
+  // node descriptors for every node touched by the plan
+  for (int n : plan.stepNodes) fillNodeDev(e, n);
+  CK(cudaMemcpyAsync(e->dNodes, e->hNodes.data(), sizeof(NodeDev) * e->nNodes, cudaMemcpyHostToDevice, e->stream));
+  // accumulators of the nodes about to be recomputed start from zero
+  if (!plan.stepNodes.empty()) {
+    const int n = (int)plan.stepNodes.size();
+    k_reset_stats<<<(n + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->dStepNodes, n);
+    CK(cudaGetLastError());
+  }
+  RunCtx c;
+  makeCtx(e, c);
+  e->info = dcsmc_run_info{};
+  e->info.poolBytes = (int64_t)e->poolBytes;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  for (auto& s : plan.steps) {
+    switch (e->opt.rngMode) {
+      case DCSMC_RNG_PHILOX: rc = launchStep<RNG_PHILOX>(e, c, s); break;
+      case DCSMC_RNG_INJECTED: rc = launchStep<RNG_INJECTED>(e, c, s); break;
+      default: rc = launchStep<RNG_JAVA>(e, c, s); break;
+    }
+    if (rc) return rc;
+    e->info.levelBatches++;
+    e->info.nodesProcessed += s.count;
+    for (int k = 0; k < s.count; ++k) {
+      const int n = plan.stepNodes[s.offset + k];
+      const int64_t C = nChildrenOf(e, n);
+      e->info.algorithmicBytes +=
+          (int64_t)N * (40 * C + 184 + (e->opt.resamplingScheme == DCSMC_MULTINOMIAL ? 16 : 0));
+    }
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  // fetch stats of all nodes (small)
+  std::vector<NodeStats> hs(e->nNodes);
+  CK(cudaMemcpyAsync(hs.data(), e->dStats, sizeof(NodeStats) * e->nNodes, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->info.deviceMs = ms;
+  e->info.particleUpdates = e->info.nodesProcessed * (int64_t)N;
+  for (int n = 0; n < e->nNodes; ++n) {
+    dcsmc_node_stats_t& o = e->hStats[n];
+    o.ess = hs[n].ess;
+    o.relEss = hs[n].relEss;
+    o.logNormEstimate = hs[n].logZ;
+    o.logScaling = hs[n].logScaling;
+    o.resampled = hs[n].resampled == RES_WEIGHTED ? 0 : 1;
+    o.done = hs[n].done;
+  }
+  if (e->profile) {
+    for (auto& pe : e->profEvents) {
+      float t = 0;
+      cudaEventElapsedTime(&t, pe.second.first, pe.second.second);
+      e->profMs[pe.first] += t;
+      e->profLaunches[pe.first]++;
+      cudaEventDestroy(pe.second.first);
+      cudaEventDestroy(pe.second.second);
+    }
+    e->profEvents.clear();
+  }
+  return DCSMC_OK;
+}
+
+int prepare(dcsmc_engine* e) {
+  int rc;
+  if ((rc = ensureDevice(e))) return rc;
+  if ((rc = validateForRun(e))) return rc;
+  e->Npad = (int)alignUp((size_t)e->opt.nParticles, 32);
+  if ((rc = uploadTables(e))) return rc;
+  if ((rc = uploadInjected(e))) return rc;
+  if ((rc = ensurePool(e))) return rc;
+  return DCSMC_OK;
+}
+
+int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
+  int rc;
+  if ((rc = prepare(e))) return rc;
+  Plan plan;
+  if ((rc = planRoots(e, roots, plan))) return rc;
+  return executePlan(e, plan);
+}
+
+}  // namespace
+
+// =================================== C ABI ====================================================
+
+extern "C" {
+
+int32_t dcsmc_abi_version(void) { return DCSMC_ABI_VERSION; }
+
+int32_t dcsmc_options_default(dcsmc_options* o) {
+  if (!o) return DCSMC_EINVAL;
+  memset(o, 0, sizeof *o);
+  o->masterRandomSeed = 31;              // DCOptions.java:16
+  o->nParticles = 1000;                  // :19
+  o->resamplingScheme = DCSMC_MULTINOMIAL;  // :22
+  o->relativeEssThreshold = 1.0 + 1e-10; // :25  1.0 + NumericalUtils.THRESHOLD (always resample)
+  o->clusterSubGroup = 1;
+  o->nThreadsPerNode = 1;
+  o->minimumNumberOfClusterMembersToStart = 1;
+  o->maximumTimeToWaitInMinutes = 1;
+  o->maximumDistributionDepth = 0x7fffffff;  // Integer.MAX_VALUE, :41
+  o->indexInCluster = 1;
+  o->device = 0;
+  o->rngMode = DCSMC_RNG_PHILOX;
+  o->sumMode = DCSMC_SUM_EXACT;
+  o->maxBetaAttempts = 32;
+  o->retainPopulations = 0;
+  o->memoryBudgetBytes = 0;
+  return DCSMC_OK;
+}
+
+const char* dcsmc_last_error(const dcsmc_engine* e) { return e ? e->err.c_str() : g_createError.c_str(); }
+
+int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
+  if (!opt || !out) {
+    g_createError = "dcsmc_create: null argument";
+    return DCSMC_EINVAL;
+  }
+  *out = nullptr;
+  if (opt->nParticles < 1 || opt->nParticles >= (1 << 24)) {
+    g_createError = "nParticles must be in [1, 2^24)";
+    return DCSMC_EINVAL;
+  }
+  if (opt->maxBetaAttempts < 1) {
+    g_createError = "maxBetaAttempts must be >= 1";
+    return DCSMC_EINVAL;
+  }
+  if (opt->sumMode != DCSMC_SUM_EXACT) {
+    g_createError = "only DCSMC_SUM_EXACT is implemented";
+    return DCSMC_EINVAL;
+  }
+  int nDev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&nDev);
+  if (ce != cudaSuccess || nDev <= 0 || opt->device >= nDev) {
+    g_createError = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                    (ce != cudaSuccess ? cudaGetErrorString(ce) : "device ordinal out of range");
+    return DCSMC_ECUDA;
+  }
+  dcsmc_engine* e = new dcsmc_engine();
+  e->opt = *opt;
+  if (cudaSetDevice(opt->device) != cudaSuccess || cudaStreamCreate(&e->stream) != cudaSuccess ||
+      cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+    g_createError = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete e;
+    return DCSMC_ECUDA;
+  }
+  *out = e;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_destroy(dcsmc_engine* e) {
+  if (!e) return DCSMC_OK;
+  cudaSetDevice(e->opt.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (double* p : e->injDev)
+    if (p) cudaFree(p);
+  void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dInj, e->dJavaState,
+                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root, const int32_t* childOffsets,
+                       const int32_t* children) {
+  if (!e) return DCSMC_EINVAL;
+  if (nNodes < 1 || !childOffsets || root < 0 || root >= nNodes)
+    return e->fail(DCSMC_EINVAL, "dcsmc_set_tree: bad arguments");
+  if (childOffsets[0] != 0) return e->fail(DCSMC_EINVAL, "childOffsets[0] must be 0");
+  const int nEdges = childOffsets[nNodes];
+  if (nEdges != nNodes - 1) return e->fail(DCSMC_EINVAL, "a tree with %d nodes needs %d edges, got %d", nNodes, nNodes - 1, nEdges);
+  if (nEdges > 0 && !children) return e->fail(DCSMC_EINVAL, "children is null");
+  std::vector<int32_t> parent(nNodes, -1);
+  for (int n = 0; n < nNodes; ++n) {
+    if (childOffsets[n + 1] < childOffsets[n]) return e->fail(DCSMC_EINVAL, "childOffsets not monotone");
+    for (int c = childOffsets[n]; c < childOffsets[n + 1]; ++c) {
+      const int ch = children[c];
+      if (ch < 0 || ch >= nNodes || ch == root || parent[ch] != -1)
+        return e->fail(DCSMC_EINVAL, "node %d: invalid or duplicate child %d", n, ch);
+      parent[ch] = n;
+    }
+  }
+  // heights (leaf = 0) via reverse BFS order
+  std::vector<int> order;
+  order.reserve(nNodes);
+  order.push_back(root);
+  for (size_t k = 0; k < order.size(); ++k)
+    for (int c = childOffsets[order[k]]; c < childOffsets[order[k] + 1]; ++c) order.push_back(children[c]);
+  if ((int)order.size() != nNodes) return e->fail(DCSMC_EINVAL, "tree is not connected");
+  std::vector<int32_t> height(nNodes, 0);
+  for (int k = nNodes - 1; k > 0; --k) {
+    const int n = order[k];
+    height[parent[n]] = std::max(height[parent[n]], height[n] + 1);
+  }
+  e->nNodes = nNodes;
+  e->root = root;
+  e->childOffsets.assign(childOffsets, childOffsets + nNodes + 1);
+  e->children.assign(children, children + nEdges);
+  e->parent = parent;
+  e->height = height;
+  e->javaHash.clear();
+  e->injHost.clear();
+  for (double* p : e->injDev)
+    if (p) cudaFree(p);
+  e->injDev.clear();
+  if (e->pool) {
+    cudaFree(e->pool);
+    e->pool = nullptr;
+  }
+  e->tablesDirty = true;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_set_node_seeds(dcsmc_engine* e, const int32_t* h) {
+  if (!e) return DCSMC_EINVAL;
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree first");
+  if (!h) return e->fail(DCSMC_EINVAL, "null hash codes");
+  e->javaHash.assign(h, h + e->nNodes);
+  e->tablesDirty = true;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_set_multilevel_model(dcsmc_engine* e, const int32_t* leafKind, const int32_t* nTrials,
+                                   const int32_t* nSuccesses, const double* leafObs, double variancePrior) {
+  if (!e) return DCSMC_EINVAL;
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree first");
+  if (!(variancePrior > 0)) return e->fail(DCSMC_EINVAL, "variancePrior must be > 0");
+  const int nN = e->nNodes;
+  e->leafKind.assign(nN, DCSMC_LEAF_BINOMIAL);
+  if (leafKind) e->leafKind.assign(leafKind, leafKind + nN);
+  e->nTrials.assign(nN, 0);
+  e->nSuccesses.assign(nN, 0);
+  e->leafObs.assign(nN, 0.0);
+  if (leafObs) e->leafObs.assign(leafObs, leafObs + nN);
+  for (int n = 0; n < nN; ++n) {
+    if (e->childOffsets[n + 1] != e->childOffsets[n]) continue;
+    if (e->leafKind[n] == DCSMC_LEAF_BINOMIAL) {
+      if (!nTrials || !nSuccesses) return e->fail(DCSMC_EINVAL, "binomial leaves need nTrials/nSuccesses");
+      // DivideConquerMCAlgorithm.logBinomialPr :595-596 throws on these
+      if (nTrials[n] < 0 || nSuccesses[n] < 0 || nSuccesses[n] > nTrials[n])
+        return e->fail(DCSMC_EINVAL, "leaf %d: invalid (nTrials=%d, nSuccesses=%d)", n, nTrials[n], nSuccesses[n]);
+      e->nTrials[n] = nTrials[n];
+      e->nSuccesses[n] = nSuccesses[n];
+    } else if (e->leafKind[n] != DCSMC_LEAF_GAUSS_OBS) {
+      return e->fail(DCSMC_EINVAL, "leaf %d: unknown leaf kind %d", n, e->leafKind[n]);
+    }
+  }
+  e->model = DCSMC_MODEL_MULTILEVEL;
+  e->rate = variancePrior;
+  if (e->pool) {
+    cudaFree(e->pool);
+    e->pool = nullptr;
+  }
+  e->tablesDirty = true;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_set_markov_model(dcsmc_engine* e, int32_t nStates, const double* transition, const double* prior) {
+  if (!e) return DCSMC_EINVAL;
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree first");
+  // TestUtilities.checkValidMarkovChain (TestUtilities.java:76-82)
+  if (nStates < 1 || !transition || !prior) return e->fail(DCSMC_EINVAL, "bad Markov model");
+  e->model = DCSMC_MODEL_MARKOV;
+  e->nStates = nStates;
+  e->markovT.assign(transition, transition + (size_t)nStates * nStates);
+  e->markovPrior.assign(prior, prior + nStates);
+  if (e->pool) {
+    cudaFree(e->pool);
+    e->pool = nullptr;
+  }
+  e->tablesDirty = true;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_slots_per_particle(const dcsmc_engine* e, int32_t node, int32_t* slots) {
+  if (!e || !slots) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes || e->model < 0) return e->fail(DCSMC_EINVAL, "bad node or no model");
+  *slots = slotsPerParticle(e, node);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_inject_uniforms(dcsmc_engine* e, int32_t node, const double* u, int64_t n) {
+  if (!e) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes || e->model < 0) return e->fail(DCSMC_EINVAL, "bad node or no model");
+  if (e->opt.rngMode != DCSMC_RNG_INJECTED) return e->fail(DCSMC_ESTATE, "engine was not created with DCSMC_RNG_INJECTED");
+  const int64_t need = (int64_t)e->opt.nParticles * slotsPerParticle(e, node) + e->opt.nParticles;
+  if (!u || n < need) return e->fail(DCSMC_EINVAL, "node %d needs %lld uniforms, got %lld", node, (long long)need, (long long)n);
+  if ((int)e->injHost.size() != e->nNodes) e->injHost.resize(e->nNodes);
+  e->injHost[node].assign(u, u + need);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_run(dcsmc_engine* e) {
+  if (!e) return DCSMC_EINVAL;
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
+  // a fresh run recomputes everything
+  std::fill(e->resident.begin(), e->resident.end(), 0);
+  e->freeBySize.clear();
+  e->poolTop = 0;
+  return runRoots(e, std::vector<int>{e->root});
+}
+
+int32_t dcsmc_run_subtrees(dcsmc_engine* e, const int32_t* roots, int32_t nRoots) {
+  if (!e) return DCSMC_EINVAL;
+  if (!roots || nRoots < 0) return e->fail(DCSMC_EINVAL, "bad roots");
+  std::vector<int> r(roots, roots + nRoots);
+  for (int x : r)
+    if (x < 0 || x >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad root %d", x);
+  return runRoots(e, r);
+}
+
+int32_t dcsmc_run_nodes(dcsmc_engine* e, const int32_t* nodes, int32_t nNodes) {
+  // children resident => collectSubtree stops at them, so this is the same planner
+  return dcsmc_run_subtrees(e, nodes, nNodes);
+}
+
+int32_t dcsmc_node_stats(const dcsmc_engine* e, int32_t node, dcsmc_node_stats_t* out) {
+  if (!e || !out) return DCSMC_EINVAL;
+  if (node < 0 || node >= (int)e->hStats.size()) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  *out = e->hStats[node];
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out) {
+  if (!e || !out) return DCSMC_EINVAL;
+  if ((int)e->hStats.size() != e->nNodes) return e->fail(DCSMC_ESTATE, "no run yet");
+  memcpy(out, e->hStats.data(), sizeof(dcsmc_node_stats_t) * e->nNodes);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* state, int32_t* istate, double* weights) {
+  if (!e) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+    return e->fail(DCSMC_ESTATE, "population of node %d is not resident (consumed by its parent, or not computed)", node);
+  CK(cudaSetDevice(e->opt.device));
+  const int N = e->opt.nParticles;
+  double* dS = nullptr;
+  int32_t* dI = nullptr;
+  double* dW = nullptr;
+  if (state) CK(cudaMalloc((void**)&dS, sizeof(double) * 6 * N));
+  if (istate) CK(cudaMalloc((void**)&dI, sizeof(int32_t) * N));
+  if (weights) CK(cudaMalloc((void**)&dW, sizeof(double) * N));
+  RunCtx c;
+  makeCtx(e, c);
+  e->info.kernelLaunches++;
+  k_materialise<<<(N + 255) / 256, 256, 0, e->stream>>>(c, node, dS, dI, dW, (size_t)N);
+  CK(cudaGetLastError());
+  if (state) CK(cudaMemcpyAsync(state, dS, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, e->stream));
+  if (istate) CK(cudaMemcpyAsync(istate, dI, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, e->stream));
+  if (weights) CK(cudaMemcpyAsync(weights, dW, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (dS) cudaFree(dS);
+  if (dI) cudaFree(dI);
+  if (dW) cudaFree(dW);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre, int32_t* istatePre,
+                              double* logWeights, int32_t* ancestors) {
+  if (!e) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  if (!e->opt.retainPopulations) return e->fail(DCSMC_ESTATE, "dcsmc_debug_copy_node needs retainPopulations=1");
+  if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+    return e->fail(DCSMC_ESTATE, "node %d not computed", node);
+  CK(cudaSetDevice(e->opt.device));
+  const int N = e->opt.nParticles;
+  const size_t NP = (size_t)e->Npad;
+  const NodeDev& d = e->hNodes[node];
+  if (statePre) {
+    const double nanv = std::nan("");
+    if (!d.state) {
+      for (size_t k = 0; k < (size_t)6 * N; ++k) statePre[k] = 0.0;
+    } else if (d.kind == KIND_INTERNAL) {
+      for (int col = 0; col < 6; ++col)
+        CK(cudaMemcpyAsync(statePre + (size_t)col * N, d.state + col * NP, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+      CK(cudaMemcpyAsync(statePre, d.state, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaMemcpyAsync(statePre + (size_t)3 * N, d.state + NP, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+      for (int i = 0; i < N; ++i) {
+        statePre[(size_t)1 * N + i] = 0.0;
+        statePre[(size_t)2 * N + i] = 0.0;
+        statePre[(size_t)4 * N + i] = 0.0;
+        statePre[(size_t)5 * N + i] = nanv;
+      }
+    }
+  }
+  if (istatePre) {
+    if (d.istate)
+      CK(cudaMemcpyAsync(istatePre, d.istate, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, e->stream));
+    else
+      memset(istatePre, 0, sizeof(int32_t) * N);
+  }
+  if (logWeights) CK(cudaMemcpyAsync(logWeights, d.logw, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (ancestors) {
+    if (e->hStats[node].resampled) {
+      CK(cudaMemcpy(ancestors, d.anc, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+    } else {
+      for (int i = 0; i < N; ++i) ancestors[i] = i;
+    }
+  }
+  return DCSMC_OK;
+}
+
+int64_t dcsmc_population_packed_bytes(const dcsmc_engine* e) {
+  if (!e) return 0;
+  const size_t NP = alignUp((size_t)e->opt.nParticles, 32);
+  return (int64_t)(256 + NP * 8 * 7 + NP * 4);
+}
+
+int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t, void*) {
+  if (!e) return DCSMC_EINVAL;
+  return e->fail(DCSMC_EINVAL, "dcsmc_population_pack: not implemented yet");
+}
+int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t, const void*) {
+  if (!e) return DCSMC_EINVAL;
+  return e->fail(DCSMC_EINVAL, "dcsmc_population_unpack: not implemented yet");
+}
+int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node) {
+  if (!e) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes || e->resident.empty()) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  poolFree(e, node);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_last_run_info(const dcsmc_engine* e, dcsmc_run_info* out) {
+  if (!e || !out) return DCSMC_EINVAL;
+  *out = e->info;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_profile_enable(dcsmc_engine* e, int32_t enable) {
+  if (!e) return DCSMC_EINVAL;
+  e->profile = enable != 0;
+  for (int k = 0; k < DCSMC_K_COUNT; ++k) {
+    e->profMs[k] = 0;
+    e->profLaunches[k] = 0;
+  }
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_profile_get(const dcsmc_engine* e, int32_t cls, double* ms, int64_t* launches) {
+  if (!e) return DCSMC_EINVAL;
+  if (cls < 0 || cls >= DCSMC_K_COUNT) return e->fail(DCSMC_EINVAL, "bad kernel class");
+  if (ms) *ms = e->profMs[cls];
+  if (launches) *launches = e->profLaunches[cls];
+  return DCSMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+"""Thin object wrapper over the C ABI (include/dcsmc.h). One Engine == one dcsmc_engine handle."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi as F
+
+
+def _ptr(a: Optional[np.ndarray], ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Engine:
+    def __init__(self, **opts):
+        L = F.lib()
+        o = F.Options()
+        L.dcsmc_options_default(C.byref(o))
+        for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown option {k}")
+            setattr(o, k, v)
+        self.options = o
+        h = C.c_void_p()
+        rc = L.dcsmc_create(C.byref(o), C.byref(h))
+        if rc != 0:
+            raise F.DcsmcError(rc, L.dcsmc_last_error(None).decode())
+        self._h = h
+        self._L = L
+        self.nNodes = 0
+        self.N = o.nParticles
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise F.DcsmcError(rc, self._L.dcsmc_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dcsmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- topology / model --------------------------------------------------------------------------
+    def set_tree(self, csr):
+        off = np.ascontiguousarray(csr.childOffsets, dtype=np.int32)
+        ch = np.ascontiguousarray(csr.children if len(csr.children) else np.zeros(1, np.int32), dtype=np.int32)
+        self._ck(self._L.dcsmc_set_tree(self._h, csr.nNodes, 0, _ptr(off, C.c_int32), _ptr(ch, C.c_int32)))
+        self.nNodes = csr.nNodes
+        h = np.ascontiguousarray(csr.javaHash, dtype=np.int32)
+        self._ck(self._L.dcsmc_set_node_seeds(self._h, _ptr(h, C.c_int32)))
+
+    def set_multilevel_model(self, nTrials=None, nSuccesses=None, leafKind=None, leafObs=None, variancePrior=1.0):
+        a = lambda x, dt: None if x is None else np.ascontiguousarray(x, dtype=dt)
+        lk, nt, ns, lo = a(leafKind, np.int32), a(nTrials, np.int32), a(nSuccesses, np.int32), a(leafObs, np.float64)
+        self._ck(self._L.dcsmc_set_multilevel_model(
+            self._h, _ptr(lk, C.c_int32), _ptr(nt, C.c_int32), _ptr(ns, C.c_int32), _ptr(lo, C.c_double),
+            float(variancePrior)))
+
+    def set_markov_model(self, transition, prior):
+        t = np.ascontiguousarray(transition, dtype=np.float64)
+        p = np.ascontiguousarray(prior, dtype=np.float64)
+        self._ck(self._L.dcsmc_set_markov_model(self._h, len(p), _ptr(t, C.c_double), _ptr(p, C.c_double)))
+
+    def slots_per_particle(self, node: int) -> int:
+        s = C.c_int32()
+        self._ck(self._L.dcsmc_slots_per_particle(self._h, node, C.byref(s)))
+        return s.value
+
+    def inject_uniforms(self, node: int, u: np.ndarray):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        self._ck(self._L.dcsmc_inject_uniforms(self._h, node, _ptr(u, C.c_double), len(u)))
+
+    # -- execution -----------------------------------------------------------------------------------
+    def run(self):
+        self._ck(self._L.dcsmc_run(self._h))
+
+    def run_subtrees(self, roots: Sequence[int]):
+        r = np.ascontiguousarray(roots, dtype=np.int32)
+        self._ck(self._L.dcsmc_run_subtrees(self._h, _ptr(r, C.c_int32), len(r)))
+
+    def run_nodes(self, nodes: Sequence[int]):
+        r = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._ck(self._L.dcsmc_run_nodes(self._h, _ptr(r, C.c_int32), len(r)))
+
+    # -- results ---------------------------------------------------------------------------------------
+    def node_stats(self, node: int) -> F.NodeStats:
+        s = F.NodeStats()
+        self._ck(self._L.dcsmc_node_stats(self._h, node, C.byref(s)))
+        return s
+
+    def all_node_stats(self) -> Dict[str, np.ndarray]:
+        arr = (F.NodeStats * self.nNodes)()
+        self._ck(self._L.dcsmc_all_node_stats(self._h, arr))
+        raw = np.frombuffer(arr, dtype=np.dtype([
+            ("ess", "f8"), ("relEss", "f8"), ("logNormEstimate", "f8"), ("logScaling", "f8"),
+            ("resampled", "i4"), ("done", "i4")]))
+        return {k: raw[k].copy() for k in raw.dtype.names}
+
+    def population(self, node: int, state=True, istate=False, weights=True):
+        N = self.N
+        st = np.empty((6, N)) if state else None
+        ist = np.empty(N, np.int32) if istate else None
+        w = np.empty(N) if weights else None
+        self._ck(self._L.dcsmc_population_copy_to_host(
+            self._h, node, _ptr(st, C.c_double), _ptr(ist, C.c_int32), _ptr(w, C.c_double)))
+        return st, ist, w
+
+    def debug_node(self, node: int):
+        N = self.N
+        st = np.empty((6, N))
+        ist = np.empty(N, np.int32)
+        lw = np.empty(N)
+        anc = np.empty(N, np.int32)
+        self._ck(self._L.dcsmc_debug_copy_node(
+            self._h, node, _ptr(st, C.c_double), _ptr(ist, C.c_int32), _ptr(lw, C.c_double), _ptr(anc, C.c_int32)))
+        return st, ist, lw, anc
+
+    def packed_bytes(self) -> int:
+        return int(self._L.dcsmc_population_packed_bytes(self._h))
+
+    def pack(self, node: int, device_ptr: int):
+        self._ck(self._L.dcsmc_population_pack(self._h, node, C.c_void_p(device_ptr)))
+
+    def unpack(self, node: int, device_ptr: int):
+        self._ck(self._L.dcsmc_population_unpack(self._h, node, C.c_void_p(device_ptr)))
+
+    def release(self, node: int):
+        self._ck(self._L.dcsmc_population_release(self._h, node))
+
+    def run_info(self) -> F.RunInfo:
+        r = F.RunInfo()
+        self._ck(self._L.dcsmc_last_run_info(self._h, C.byref(r)))
+        return r
+
+    def profile_enable(self, on: bool = True):
+        self._ck(self._L.dcsmc_profile_enable(self._h, 1 if on else 0))
+
+    def profile(self) -> Dict[str, Dict[str, float]]:
+        out = {}
+        for k, name in enumerate(F.K_NAMES):
+            ms, n = C.c_double(), C.c_int64()
+            self._ck(self._L.dcsmc_profile_get(self._h, k, C.byref(ms), C.byref(n)))
+            out[name] = {"ms": ms.value, "launches": n.value}
+        return out

@@ -1,0 +1,231 @@
+/*
+ * dcsmc.h — C ABI of the B200-native DC-SMC node engine (libdcsmc.so).
+ *
+ * This is the drop-in boundary for the per-tree-node DC-SMC step of
+ * alexandrebouchard/divide-and-conquer-smc. The reference's FFI-free Java path is
+ *     DistributedDC.start() -> DCRecursionTask.run() -> DCRecursion.dcRecurse()
+ *         -> DCProposal.propose() per particle -> ParticlePopulation.resample()
+ * A per-particle JVM callback cannot be a GPU boundary, so the boundary is one level up:
+ * "run the node step of a known proposal family for a whole (sub)tree, level-batched".
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/src/main/java). INTEGRATION.md shows the JNI / Panama binding.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a
+ * DCSMC_E* code, and dcsmc_last_error() returns the message (no exception crosses the
+ * ABI; the reference throws bare RuntimeExceptions, e.g. DCRecursion.java:43,50).
+ * One engine handle is driven by one host thread at a time; distinct handles are
+ * independent (this lifts the reference's one-instance-per-JVM limit,
+ * DistributedDC.java:63-67). The engine owns all device memory; particles never cross
+ * the ABI unless the caller asks for a copy. There is NO CPU fallback: dcsmc_create
+ * fails when no CUDA device is present.
+ */
+#ifndef DCSMC_H
+#define DCSMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCSMC_ABI_VERSION 1
+
+enum {
+  DCSMC_OK = 0,
+  DCSMC_EINVAL = 1,   /* bad argument / bad state (reference: RuntimeException) */
+  DCSMC_ECUDA = 2,    /* CUDA runtime error */
+  DCSMC_ENOMEM = 3,   /* population pool does not fit the memory budget */
+  DCSMC_ESTATE = 4    /* call sequence violated (e.g. run before set_tree) */
+};
+
+/* bayonet.smc.ResamplingScheme as used by DCOptions.resamplingScheme (DCOptions.java:22) */
+enum { DCSMC_MULTINOMIAL = 0, DCSMC_STRATIFIED = 1 };
+
+/* source of the uniforms (engine extension; the reference has java.util.Random only) */
+enum {
+  DCSMC_RNG_PHILOX = 0,   /* counter-based Philox4x32-10 keyed by (masterRandomSeed, node) */
+  DCSMC_RNG_INJECTED = 1, /* caller-supplied uniform stream per node (parity runs) */
+  DCSMC_RNG_JAVA = 2      /* java.util.Random(seed(node)) reproduced with LCG jump-ahead;
+                             only for proposals with fixed draw counts (internal nodes,
+                             Markov model); binomial leaves are rejected */
+};
+
+/* proposal families = implementations of dc.DCProposalFactory shipped with the reference */
+enum {
+  DCSMC_MODEL_MULTILEVEL = 0, /* prototype.adaptor.MultiLevelProposalFactory */
+  DCSMC_MODEL_MARKOV = 1      /* Doc.markovChainNaiveProposalFactory (src/test/java/dc/Doc.java:206) */
+};
+
+enum { DCSMC_LEAF_BINOMIAL = 0, DCSMC_LEAF_GAUSS_OBS = 1 };
+
+/* summation contract of the normaliser / CDF (DESIGN.md "Numerics contract") */
+enum {
+  DCSMC_SUM_EXACT = 0, /* order-independent fixed-point sums (default, fast) */
+  DCSMC_SUM_JAVA = 1   /* strictly sequential fp64 sums, the reference's own order */
+};
+
+/* dc.DCOptions (dc/DCOptions.java:15-45), field for field, then engine extensions. */
+typedef struct dcsmc_options {
+  int64_t masterRandomSeed;                     /* :16  default 31 */
+  int32_t nParticles;                           /* :19  default 1000 */
+  int32_t resamplingScheme;                     /* :22  default MULTINOMIAL */
+  double relativeEssThreshold;                  /* :25  default 1 + THRESHOLD (always resample) */
+  int32_t clusterSubGroup;                      /* :29  accepted, unused */
+  int32_t nThreadsPerNode;                      /* :32  accepted, unused (the GPU is the pool) */
+  int32_t minimumNumberOfClusterMembersToStart; /* :35  accepted, unused */
+  int32_t maximumTimeToWaitInMinutes;           /* :38  accepted, unused */
+  int32_t maximumDistributionDepth;             /* :41  cut depth for subtree sharding */
+  int32_t indexInCluster;                       /* :45  accepted, unused */
+  /* ---- engine extensions ---- */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t rngMode;           /* DCSMC_RNG_* */
+  int32_t sumMode;           /* DCSMC_SUM_* */
+  int32_t maxBetaAttempts;   /* Beta rejection-sampler attempt cap; slot budget per leaf
+                                particle = 2*maxBetaAttempts uniforms (default 32) */
+  int32_t retainPopulations; /* 1: keep every node's population resident (debug/parity) */
+  int32_t reserved0;
+  int64_t memoryBudgetBytes; /* 0: use 85% of free device memory */
+} dcsmc_options;
+
+typedef struct dcsmc_engine dcsmc_engine;
+
+/* ---- life cycle --------------------------------------------------------------------- */
+
+/* new DCOptions() defaults (DCOptions.java:15-45) + engine defaults. */
+int32_t dcsmc_options_default(dcsmc_options* opt);
+
+/* DistributedDC.createInstance(options, proposalFactory, tree) is split into
+ * dcsmc_create + dcsmc_set_tree + dcsmc_set_*_model (DistributedDC.java:58-70). */
+int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out);
+int32_t dcsmc_destroy(dcsmc_engine* e);
+/* message of the last failing call on this handle (or of dcsmc_create when e == NULL) */
+const char* dcsmc_last_error(const dcsmc_engine* e);
+int32_t dcsmc_abi_version(void);
+
+/* ---- topology and model --------------------------------------------------------------- */
+
+/* bayonet DirectedTree<N> passed to createInstance: CSR with children in the reference's
+ * order (DCRecursionTask.java:51; the order is the fold order of
+ * BrownianModelCalculator.combine and therefore visible in floating point). */
+int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root,
+                       const int32_t* childOffsets, const int32_t* children);
+
+/* N.hashCode() per node, feeding DCRecursionTask.getRandom (DCRecursionTask.java:98-106):
+ * seed = 31*(31*1 + masterRandomSeed) + hashCode. Used by DCSMC_RNG_JAVA. */
+int32_t dcsmc_set_node_seeds(dcsmc_engine* e, const int32_t* javaHashCodes);
+
+/* prototype.adaptor.MultiLevelProposalFactory (MultiLevelProposalFactory.java:22-52):
+ * per-node arrays (entries of internal nodes ignored); leafKind/leafObs may be NULL
+ * (all leaves binomial). variancePrior is the Exponential rate (default 1.0). */
+int32_t dcsmc_set_multilevel_model(dcsmc_engine* e, const int32_t* leafKind,
+                                   const int32_t* nTrials, const int32_t* nSuccesses,
+                                   const double* leafObs, double variancePrior);
+
+/* Doc.markovChainNaiveProposalFactory (Doc.java:162-225): row-major transition matrix. */
+int32_t dcsmc_set_markov_model(dcsmc_engine* e, int32_t nStates, const double* transition,
+                               const double* prior);
+
+/* Number of uniforms a particle of this node may draw in propose() (slot stride S); the
+ * node's stream is [N*S proposal slots | N resampling darts]. */
+int32_t dcsmc_slots_per_particle(const dcsmc_engine* e, int32_t node, int32_t* slots);
+
+/* Replaces the `Random random` argument of DCProposal.propose / ParticlePopulation.resample
+ * (DCProposal.java:28, DCRecursion.java:31) for DCSMC_RNG_INJECTED: host buffer of
+ * N*S + N uniforms in [0,1) for this node; copied to the device. */
+int32_t dcsmc_inject_uniforms(dcsmc_engine* e, int32_t node, const double* u, int64_t n);
+
+/* ---- execution ------------------------------------------------------------------------ */
+
+/* DistributedDC.start() (DistributedDC.java:87-92): run DCRecursion.dcRecurse for every
+ * node, bottom-up, all sibling nodes of a level in one batch of launches. Blocking. */
+int32_t dcsmc_run(dcsmc_engine* e);
+
+/* DCRecursionTask.run(node, false) for several subtree roots at once
+ * (DCRecursionTask.java:48-75; DistributedDC.populateInitialTasks :165-175): runs every
+ * node under each root; the roots' populations stay resident. */
+int32_t dcsmc_run_subtrees(dcsmc_engine* e, const int32_t* roots, int32_t nRoots);
+
+/* DCRecursionTask.run(node, true) (:48-66) for nodes whose children populations are
+ * already resident (computed here or installed with dcsmc_population_unpack). */
+int32_t dcsmc_run_nodes(dcsmc_engine* e, const int32_t* nodes, int32_t nNodes);
+
+/* ---- results -------------------------------------------------------------------------- */
+
+/* What DCProcessor.process(populationBeforeResampling, ..) can read
+ * (DCProcessor.java:18, DefaultProcessorFactory.java:41-54): getESS(), getRelativeESS(),
+ * logNormEstimate(), plus logScaling and whether resample() ran (DCRecursion.java:29-31). */
+typedef struct dcsmc_node_stats_t {
+  double ess;
+  double relEss;
+  double logNormEstimate;
+  double logScaling;
+  int32_t resampled;
+  int32_t done;
+} dcsmc_node_stats_t;
+
+int32_t dcsmc_node_stats(const dcsmc_engine* e, int32_t node, dcsmc_node_stats_t* out);
+/* all nodes at once: out[nNodes] */
+int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out);
+
+/* DistributedDC.getRootPopulation() / ParticlePopulation accessors (DistributedDC.java:107;
+ * SURVEY §8a row P): copies the node's population AFTER the node step (resampled if
+ * resampling ran) to host buffers; any pointer may be NULL.
+ *   state   [6][N]: mean, msgVar, logLik, descObs, descVar, variance (multilevel model)
+ *   istate  [N]   : Markov particle
+ *   weights [N]   : getNormalizedWeight(i) */
+int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* state,
+                                      int32_t* istate, double* weights);
+
+/* Parity/debug view of a node (needs retainPopulations=1): the population BEFORE
+ * resampling, the raw log weights and the ancestor indices (identity if not resampled). */
+int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre,
+                              int32_t* istatePre, double* logWeights, int32_t* ancestors);
+
+/* ---- moving populations between engines (replaces Hazelcast populations.put/remove,
+ * DCRecursionTask.java:37,113) ---------------------------------------------------------- */
+
+/* bytes of one packed population (post-node-step, SoA) */
+int64_t dcsmc_population_packed_bytes(const dcsmc_engine* e);
+/* write the node's packed population into a DEVICE buffer of that size */
+int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t node, void* deviceDst);
+/* install a packed population (DEVICE buffer) as `node`'s finished population */
+int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* deviceSrc);
+/* release a node's population (the parent consumed it) */
+int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node);
+
+/* ---- measurement ---------------------------------------------------------------------- */
+
+enum {
+  DCSMC_K_LEAF = 0,     /* leaf propose (MultiLevelLeafProposal.propose) */
+  DCSMC_K_INTERNAL = 1, /* merge + propose + weight (DCRecursion.dcPropose) */
+  DCSMC_K_SCAN = 2,     /* expNormalize + CDF + ESS partials */
+  DCSMC_K_FINALIZE = 3, /* logScaling / ESS / resample decision per node */
+  DCSMC_K_DARTS = 4,    /* multinomial dart generation + bucket sort */
+  DCSMC_K_RESAMPLE = 5, /* ancestor search */
+  DCSMC_K_GATHER = 6,   /* materialise a resampled population */
+  DCSMC_K_MARKOV = 7,   /* Doc toy-model propose */
+  DCSMC_K_COUNT = 8
+};
+
+typedef struct dcsmc_run_info {
+  double deviceMs;         /* CUDA-event time of the last run call */
+  int64_t kernelLaunches;  /* kernels of this library launched by the last run call */
+  int64_t particleUpdates; /* nodes processed * nParticles */
+  int64_t nodesProcessed;
+  int64_t algorithmicBytes; /* sum over nodes of N*(40*C + 184 [+16 multinomial]) */
+  int64_t poolBytes;        /* device bytes reserved for populations */
+  int32_t levelBatches;
+  int32_t reserved;
+} dcsmc_run_info;
+
+int32_t dcsmc_last_run_info(const dcsmc_engine* e, dcsmc_run_info* out);
+
+/* per-kernel-class CUDA-event timing (adds an event pair around every launch) */
+int32_t dcsmc_profile_enable(dcsmc_engine* e, int32_t enable);
+int32_t dcsmc_profile_get(const dcsmc_engine* e, int32_t kernelClass, double* ms,
+                          int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

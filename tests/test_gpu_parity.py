@@ -1,0 +1,146 @@
+"""GPU <-> oracle parity through the C ABI (include/dcsmc.h). The oracle runs the same
+numerics contract (fdlibm elementary functions = StrictMath, exact sums), so everything is
+compared BIT-EXACT: particle states, log weights, ancestor indices, ESS, logZ.
+Tolerance for fp64: 0 ulp vs the contract oracle; 1e-9 relative vs the java-order oracle
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import dcsmc_b200 as d
+import oracle_lib as o
+from dcsmc_b200 import synth
+from dcsmc_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+T = np.array([[0.8, 0.2], [0.2, 0.8]])
+PRIOR = np.array([0.5, 0.5])
+
+
+def small_dataset(seed=7):
+    ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows(seed=seed))
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    return csr, nT, nS
+
+
+def compare_all(e, ref, csr, markov=False):
+    st = e.all_node_stats()
+    assert np.array_equal(st["resampled"], ref.resampled)
+    assert np.array_equal(st["logScaling"], ref.logScaling)
+    assert np.array_equal(st["logNormEstimate"], ref.logNormEstimate)
+    assert np.array_equal(st["ess"], ref.ess)
+    assert np.array_equal(st["relEss"], ref.relEss)
+    for n in range(csr.nNodes):
+        state, istate, lw, anc = e.debug_node(n)
+        assert np.array_equal(lw, ref.logw[n]), f"logW node {n}"
+        assert np.array_equal(anc, ref.anc[n]), f"ancestors node {n}"
+        if markov:
+            assert np.array_equal(istate, ref.istate[n]), f"istate node {n}"
+        else:
+            assert np.array_equal(state, ref.state[n], equal_nan=True), f"state node {n}"
+
+
+@pytest.mark.parametrize("N", [1, 33, 1000, 5000])
+@pytest.mark.parametrize("threshold", [1.0 + 1e-10, 0.5])
+def test_multilevel_philox_stratified_bit_exact(N, threshold):
+    csr, nT, nS = small_dataset()
+    ref = o.run(csr, N, masterRandomSeed=31, resamplingScheme=o.STRATIFIED, relativeEssThreshold=threshold,
+                rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+    with Engine(nParticles=N, masterRandomSeed=31, resamplingScheme=1, relativeEssThreshold=threshold,
+                retainPopulations=1) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        compare_all(e, ref, csr)
+        # root population == what getRootPopulation() returns
+        rs, _, rw = e.population(0)
+        assert np.array_equal(rs, ref.rootState, equal_nan=True)
+        assert np.array_equal(rw, ref.rootWeights)
+
+
+def test_multilevel_injected_stream_bit_exact():
+    """north_star: both sides driven by an identical injected uniform stream."""
+    csr, nT, nS = small_dataset(seed=11)
+    N, maxAtt = 777, 8
+    rng = np.random.default_rng(31)
+    inj = []
+    for n in range(csr.nNodes):
+        S = o.slots_per_particle(csr, n, maxBetaAttempts=maxAtt)
+        inj.append(rng.random(N * S + N))
+    ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_INJECTED, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, maxBetaAttempts=maxAtt, injected=inj, dump=True)
+    with Engine(nParticles=N, resamplingScheme=1, rngMode=1, maxBetaAttempts=maxAtt, retainPopulations=1) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        for n in range(csr.nNodes):
+            assert e.slots_per_particle(n) == o.slots_per_particle(csr, n, maxBetaAttempts=maxAtt)
+            e.inject_uniforms(n, inj[n])
+        e.run()
+        compare_all(e, ref, csr)
+    # and the java-order / libm oracle (the most literal restatement of the Java) agrees within 1e-9
+    lit = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_INJECTED, sumMode=o.SUM_JAVA,
+                elemMode=o.ELEM_LIBM, nTrials=nT, nSuccesses=nS, maxBetaAttempts=maxAtt, injected=inj, dump=True)
+    assert int((lit.anc != ref.anc).sum()) == 0
+    assert np.allclose(lit.logNormEstimate, ref.logNormEstimate, rtol=1e-9, atol=0)
+    assert np.allclose(lit.logw, ref.logw, rtol=1e-9, atol=1e-12)
+
+
+def test_markov_doc_model_philox_bit_exact():
+    csr = d.perfectBinaryTree(3).to_csr()
+    N = 20000
+    ref = o.run(csr, N, model=o.MODEL_MARKOV, resamplingScheme=o.STRATIFIED, relativeEssThreshold=0.5,
+                rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, transition=T, prior=PRIOR, dump=True)
+    with Engine(nParticles=N, resamplingScheme=1, relativeEssThreshold=0.5, retainPopulations=1) as e:
+        e.set_tree(csr)
+        e.set_markov_model(T, PRIOR)
+        e.run()
+        compare_all(e, ref, csr, markov=True)
+        assert abs(e.node_stats(0).logNormEstimate - (-3.600962588536195)) / 3.6 < 0.02
+
+
+def test_gauss_binary_tree_bit_exact():
+    """BASELINE config 4 shape (small): perfect binary tree with observed real leaves."""
+    csr, leafKind, leafObs = synth.binary_gauss_tree(5)
+    N = 2000
+    ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, leafKind=leafKind, leafObs=leafObs, dump=True)
+    with Engine(nParticles=N, resamplingScheme=1, retainPopulations=1) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(leafKind=leafKind, leafObs=leafObs)
+        e.run()
+        compare_all(e, ref, csr)
+
+
+def test_populations_are_released_without_retain():
+    csr, nT, nS = small_dataset()
+    N = 3000
+    ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
+    with Engine(nParticles=N, resamplingScheme=1) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        st = e.all_node_stats()
+        assert np.array_equal(st["logNormEstimate"], ref.logNormEstimate)
+        rs, _, rw = e.population(0)
+        assert np.array_equal(rs, ref.rootState, equal_nan=True)
+        with pytest.raises(Exception):
+            e.population(1)  # consumed by the root (DCRecursionTask.java:113)
+        # running twice gives the same answer (per-node streams, Doc.java:268)
+        e.run()
+        assert np.array_equal(e.all_node_stats()["logNormEstimate"], ref.logNormEstimate)
+
+
+def test_error_paths():
+    with Engine(nParticles=10) as e:
+        with pytest.raises(Exception):
+            e.run()  # no tree
+        csr, nT, nS = small_dataset()
+        e.set_tree(csr)
+        with pytest.raises(Exception):
+            e.run()  # no model
+        bad = nS.copy()
+        bad[np.argmax(nT > 0)] = 10 ** 6  # nSuccesses > nTrials: logBinomialPr throws (DivideConquerMCAlgorithm.java:595)
+        with pytest.raises(Exception):
+            e.set_multilevel_model(nT, bad)
