@@ -59,6 +59,8 @@ class RunInfo(C.Structure):
         ("nodesProcessed", C.c_int64),
         ("algorithmicBytes", C.c_int64),
         ("poolBytes", C.c_int64),
+        ("h2dBytes", C.c_int64),
+        ("d2hBytes", C.c_int64),
         ("levelBatches", C.c_int32),
         ("reserved", C.c_int32),
     ]
@@ -72,7 +74,7 @@ SYMBOLS = [
     "dcsmc_run_nodes", "dcsmc_node_stats", "dcsmc_all_node_stats", "dcsmc_population_copy_to_host",
     "dcsmc_debug_copy_node", "dcsmc_population_packed_bytes", "dcsmc_population_pack",
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
-    "dcsmc_profile_enable", "dcsmc_profile_get",
+    "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval",
 ]
 
 _lib = None
@@ -117,6 +119,7 @@ def lib():
     L.dcsmc_last_run_info.argtypes = [vp, P(RunInfo)]
     L.dcsmc_profile_enable.argtypes = [vp, i32]
     L.dcsmc_profile_get.argtypes = [vp, i32, P(dbl), P(i64)]
+    L.dcsmc_debug_eval.argtypes = [vp, i32, P(dbl), P(dbl), i64]
     for s in SYMBOLS:
         f = getattr(L, s)
         if s not in ("dcsmc_last_error", "dcsmc_population_packed_bytes"):

@@ -74,6 +74,7 @@ struct dcsmc_engine {
   // population pool
   char* pool = nullptr;
   size_t poolBytes = 0;
+  bool poolIsBudget = false;  // pool was capped by the memory budget
   std::multimap<size_t, size_t> freeBySize;  // bytes -> offset (exact-size free lists)
   size_t poolTop = 0;
   std::vector<Slot> slot;        // per node
@@ -87,9 +88,15 @@ struct dcsmc_engine {
   size_t cdfCap = 0;
   unsigned long long* dDesc = nullptr;  // descA | descB | ticket
   size_t descCap = 0;
+  double* dDarts = nullptr;  // multinomial: bucket-ordered darts
+  size_t dartsCap = 0;
+  int32_t* dDartInts = nullptr;  // count | cursor | offset
+  size_t dartIntsCap = 0;
+  int NB = 1;
 
   // measurement
   dcsmc_run_info info{};
+  int64_t pendingH2D = 0;  // table uploads since the last run, charged to the next run
   bool profile = false;
   double profMs[DCSMC_K_COUNT] = {0};
   int64_t profLaunches[DCSMC_K_COUNT] = {0};
@@ -134,15 +141,15 @@ int slotsPerParticle(const dcsmc_engine* e, int n) {
 
 size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// bytes of one node's resident population
+// bytes of one node's resident population. Leaves carry no log-weight column (all equal).
 size_t slotBytes(const dcsmc_engine* e, int n) {
   const size_t NP = (size_t)e->Npad;
+  const bool internal = nodeKind(e, n) == KIND_INTERNAL;
   size_t b = 0;
   if (e->model == DCSMC_MODEL_MARKOV) {
-    b = NP * 4 /*istate*/ + NP * 8 /*logw*/ + NP * 4 /*anc*/;
+    b = NP * 4 /*istate*/ + NP * 4 /*anc*/ + (internal ? NP * 8 : 0) /*logw*/;
   } else {
-    const int cols = nodeKind(e, n) == KIND_INTERNAL ? 6 : 2;
-    b = NP * 8 * cols + NP * 8 /*logw*/ + NP * 4 /*anc*/;
+    b = NP * 8 * (internal ? 6 : 2) + NP * 4 /*anc*/ + (internal ? NP * 8 : 0) /*logw*/;
   }
   return alignUp(b, 256);
 }
@@ -178,16 +185,17 @@ void fillNodeDev(dcsmc_engine* e, int n) {
   d.nChildren = nChildrenOf(e, n);
   d.kind = nodeKind(e, n);
   d.pad = 0;
+  const bool internal = d.kind == KIND_INTERNAL;
   if (e->model == DCSMC_MODEL_MARKOV) {
     d.state = nullptr;
-    d.logw = reinterpret_cast<double*>(base);
-    d.istate = reinterpret_cast<int32_t*>(base + NP * 8);
-    d.anc = reinterpret_cast<int32_t*>(base + NP * 12);
+    d.istate = reinterpret_cast<int32_t*>(base);
+    d.anc = reinterpret_cast<int32_t*>(base + NP * 4);
+    d.logw = internal ? reinterpret_cast<double*>(base + NP * 8) : nullptr;
   } else {
-    const int cols = d.kind == KIND_INTERNAL ? 6 : 2;
+    const int cols = internal ? 6 : 2;
     d.state = reinterpret_cast<double*>(base);
-    d.logw = reinterpret_cast<double*>(base + NP * 8 * cols);
-    d.anc = reinterpret_cast<int32_t*>(base + NP * 8 * (cols + 1));
+    d.anc = reinterpret_cast<int32_t*>(base + NP * 8 * cols);
+    d.logw = internal ? reinterpret_cast<double*>(base + NP * 8 * cols + NP * 4) : nullptr;
     d.istate = nullptr;
   }
 }
@@ -252,6 +260,7 @@ int uploadTables(dcsmc_engine* e) {
   CK(re((void**)&e->dJavaState, sizeof(uint64_t) * nN));
   CK(cudaMemcpyAsync(e->dChildren, e->children.data(), sizeof(int32_t) * e->children.size(),
                      cudaMemcpyHostToDevice, e->stream));
+  e->pendingH2D += (int64_t)(sizeof(int32_t) * e->children.size() + (sizeof(LeafConst) + sizeof(uint64_t)) * nN);
   std::vector<LeafConst> lc(nN);
   if (e->model == DCSMC_MODEL_MULTILEVEL)
     for (int n = 0; n < nN; ++n) leafConstFor(e, n, lc[n]);
@@ -292,6 +301,7 @@ int uploadInjected(dcsmc_engine* e) {
       CK(cudaMemcpyAsync(e->injDev[n], e->injHost[n].data(), sizeof(double) * e->injHost[n].size(),
                          cudaMemcpyHostToDevice, e->stream));
       CK(cudaStreamSynchronize(e->stream));
+      e->pendingH2D += (int64_t)(sizeof(double) * e->injHost[n].size());
       e->injHost[n].clear();
       e->injHost[n].shrink_to_fit();
     }
@@ -301,15 +311,20 @@ int uploadInjected(dcsmc_engine* e) {
 }
 
 int ensurePool(dcsmc_engine* e) {
-  if (e->pool) return DCSMC_OK;
-  size_t freeB = 0, totalB = 0;
-  CK(cudaMemGetInfo(&freeB, &totalB));
-  size_t budget = e->opt.memoryBudgetBytes > 0 ? (size_t)e->opt.memoryBudgetBytes : (size_t)(freeB * 0.85);
   // the pool never needs more than "everything resident at once"
   size_t all = 0;
   for (int n = 0; n < e->nNodes; ++n) all += slotBytes(e, n);
-  // scratch for the largest conceivable step is taken from the same budget (cdf: 8 B/particle)
+  if (e->pool && (e->poolBytes >= all || e->poolIsBudget)) return DCSMC_OK;
+  if (e->pool) {
+    cudaFree(e->pool);
+    e->pool = nullptr;
+  }
+  size_t freeB = 0, totalB = 0;
+  CK(cudaMemGetInfo(&freeB, &totalB));
+  // leave room for the per-step scratch (CDF: 8 B per particle of the largest step)
+  const size_t budget = e->opt.memoryBudgetBytes > 0 ? (size_t)e->opt.memoryBudgetBytes : (size_t)(freeB * 0.80);
   e->poolBytes = std::min(budget, all);
+  e->poolIsBudget = e->poolBytes < all;
   CK(cudaMalloc((void**)&e->pool, e->poolBytes));
   return DCSMC_OK;
 }
@@ -450,6 +465,12 @@ struct ProfScope {
   }
 };
 
+double uniformLeafLogW(const dcsmc_engine* e) {
+  // DCRecursion.java:55,63: log(1.0) + proposal log weight; leaves propose with a constant log weight
+  if (e->model == DCSMC_MODEL_MARKOV) return dc_log(1.0) + dc_log(e->markovPrior[0]);  // Doc.java:219
+  return dc_log(1.0) + 0.0;  // MultiLevelLeafProposal.java:40
+}
+
 template <int RNG>
 int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   RunCtx c = base;
@@ -461,24 +482,32 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   const int tilesR = (N + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
   const long long gridP = (long long)st.count * tilesP;
   if (gridP > 0x7fffffffLL) return e->fail(DCSMC_EINVAL, "step too large for one launch");
-  // scratch
-  const size_t needDesc = (size_t)st.count * tilesS;
-  c.descA = e->dDesc;
-  c.descB = e->dDesc + needDesc;
-  c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + 2 * needDesc);
-  CK(cudaMemsetAsync(e->dDesc, 0, (2 * needDesc + 1) * sizeof(unsigned long long), e->stream));
 
   if (e->model == DCSMC_MODEL_MARKOV) {
     ProfScope p(e, DCSMC_K_MARKOV);
     k_markov_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
   } else if (st.leaf) {
+    // each warp refills its lanes from a chunk of CH particles (see k_leaf_propose)
+    int CH = (N + LEAF_WARPS - 1) / LEAF_WARPS;
+    CH = std::min(512, std::max(32, (CH + 31) / 32 * 32));
+    const int blocksPerNode = (N + LEAF_WARPS * CH - 1) / (LEAF_WARPS * CH);
     ProfScope p(e, DCSMC_K_LEAF);
-    k_leaf_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
+    k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS,
+                          LEAF_WARPS * CH * sizeof(double), e->stream>>>(c, blocksPerNode, CH);
   } else {
     ProfScope p(e, DCSMC_K_INTERNAL);
     k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
   }
-  {
+  if (st.leaf) {
+    // all weights equal: the exact sums are known in closed form, no scan and no CDF
+    ProfScope p(e, DCSMC_K_FINALIZE);
+    k_uniform_stats<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
+  } else {
+    const size_t needDesc = (size_t)st.count * tilesS;
+    c.descA = e->dDesc;
+    c.descB = e->dDesc + needDesc;
+    c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + 2 * needDesc);
+    CK(cudaMemsetAsync(e->dDesc, 0, (2 * needDesc + 1) * sizeof(unsigned long long), e->stream));
     ProfScope p(e, DCSMC_K_SCAN);
     k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, e->stream>>>(c, tilesS);
   }
@@ -490,7 +519,27 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
     ProfScope p(e, DCSMC_K_RESAMPLE);
     k_resample_stratified<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
   } else {
-    return e->fail(DCSMC_EINVAL, "MULTINOMIAL resampling is not implemented yet");
+    const size_t nb = (size_t)st.count * c.NB;
+    c.dartCount = e->dDartInts;
+    c.dartCursor = e->dDartInts + nb;
+    c.dartOffset = e->dDartInts + 2 * nb;
+    CK(cudaMemsetAsync(e->dDartInts, 0, 2 * nb * sizeof(int32_t), e->stream));
+    {
+      ProfScope p(e, DCSMC_K_DARTS);
+      k_darts_hist<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+    }
+    {
+      ProfScope p(e, DCSMC_K_DARTS);
+      k_darts_scan<<<st.count, 256, 0, e->stream>>>(c);
+    }
+    {
+      ProfScope p(e, DCSMC_K_DARTS);
+      k_darts_scatter<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+    }
+    {
+      ProfScope p(e, DCSMC_K_RESAMPLE);
+      k_resample_multinomial<<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+    }
   }
   CK(cudaGetLastError());
   return DCSMC_OK;
@@ -521,6 +570,9 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.dN = (double)N;
   c.threshold = e->opt.relativeEssThreshold;
   c.cdf = e->dCdf;
+  c.darts = e->dDarts;
+  c.NB = e->NB;
+  c.uniformLogW = uniformLeafLogW(e);
   return DCSMC_OK;
 }
 
@@ -545,23 +597,28 @@ int validateForRun(dcsmc_engine* e) {
 int executePlan(dcsmc_engine* e, Plan& plan) {
   int rc;
   const int N = e->opt.nParticles;
-  // scratch sizing
-  size_t maxStep = 0;
-  for (auto& s : plan.steps) maxStep = std::max<size_t>(maxStep, s.count);
-  const size_t tilesS = (N + SCAN_TILE - 1) / SCAN_TILE;
-  const size_t needCdf = maxStep * (size_t)e->Npad;
-  if (needCdf > e->cdfCap) {
-    if (e->dCdf) cudaFree(e->dCdf);
-    e->dCdf = nullptr;
-    CK(cudaMalloc((void**)&e->dCdf, needCdf * sizeof(double)));
-    e->cdfCap = needCdf;
+  // scratch sizing: CDF + look-back descriptors for internal steps, darts for multinomial
+  size_t maxStep = 0, maxInternalStep = 0;
+  for (auto& s : plan.steps) {
+    maxStep = std::max<size_t>(maxStep, s.count);
+    if (!s.leaf) maxInternalStep = std::max<size_t>(maxInternalStep, s.count);
   }
-  const size_t needDesc = 2 * maxStep * tilesS + 1;
-  if (needDesc > e->descCap) {
-    if (e->dDesc) cudaFree(e->dDesc);
-    e->dDesc = nullptr;
-    CK(cudaMalloc((void**)&e->dDesc, needDesc * sizeof(unsigned long long)));
-    e->descCap = needDesc;
+  const size_t tilesS = (N + SCAN_TILE - 1) / SCAN_TILE;
+  auto grow = [&](void** p, size_t& cap, size_t need, size_t elem) -> cudaError_t {
+    if (need <= cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    cudaError_t r = cudaMalloc(p, need * elem);
+    cap = r == cudaSuccess ? need : 0;
+    return r;
+  };
+  CK(grow((void**)&e->dCdf, e->cdfCap, std::max<size_t>(1, maxInternalStep * (size_t)e->Npad), sizeof(double)));
+  CK(grow((void**)&e->dDesc, e->descCap, 2 * maxInternalStep * tilesS + 1, sizeof(unsigned long long)));
+  e->NB = 1;
+  while ((size_t)e->NB * 16 < (size_t)N) e->NB <<= 1;
+  if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL) {
+    CK(grow((void**)&e->dDarts, e->dartsCap, maxStep * (size_t)e->Npad, sizeof(double)));
+    CK(grow((void**)&e->dDartInts, e->dartIntsCap, maxStep * (3 * (size_t)e->NB + 1), sizeof(int32_t)));
   }
   if (plan.stepNodes.size() > e->stepNodesCap) {
     if (e->dStepNodes) cudaFree(e->dStepNodes);
@@ -584,6 +641,9 @@ int executePlan(dcsmc_engine* e, Plan& plan) {
   makeCtx(e, c);
   e->info = dcsmc_run_info{};
   e->info.poolBytes = (int64_t)e->poolBytes;
+  e->info.h2dBytes = e->pendingH2D + (int64_t)(plan.stepNodes.size() * sizeof(int32_t) + sizeof(NodeDev) * e->nNodes);
+  e->info.d2hBytes = (int64_t)(sizeof(NodeStats) * e->nNodes);
+  e->pendingH2D = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
   for (auto& s : plan.steps) {
     switch (e->opt.rngMode) {
@@ -728,7 +788,7 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   for (double* p : e->injDev)
     if (p) cudaFree(p);
   void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dInj, e->dJavaState,
-                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc};
+                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dDarts, e->dDartInts};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -780,10 +840,6 @@ int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root, const int3
   for (double* p : e->injDev)
     if (p) cudaFree(p);
   e->injDev.clear();
-  if (e->pool) {
-    cudaFree(e->pool);
-    e->pool = nullptr;
-  }
   e->tablesDirty = true;
   return DCSMC_OK;
 }
@@ -824,10 +880,6 @@ int32_t dcsmc_set_multilevel_model(dcsmc_engine* e, const int32_t* leafKind, con
   }
   e->model = DCSMC_MODEL_MULTILEVEL;
   e->rate = variancePrior;
-  if (e->pool) {
-    cudaFree(e->pool);
-    e->pool = nullptr;
-  }
   e->tablesDirty = true;
   return DCSMC_OK;
 }
@@ -841,10 +893,6 @@ int32_t dcsmc_set_markov_model(dcsmc_engine* e, int32_t nStates, const double* t
   e->nStates = nStates;
   e->markovT.assign(transition, transition + (size_t)nStates * nStates);
   e->markovPrior.assign(prior, prior + nStates);
-  if (e->pool) {
-    cudaFree(e->pool);
-    e->pool = nullptr;
-  }
   e->tablesDirty = true;
   return DCSMC_OK;
 }
@@ -968,7 +1016,14 @@ int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre, i
     else
       memset(istatePre, 0, sizeof(int32_t) * N);
   }
-  if (logWeights) CK(cudaMemcpyAsync(logWeights, d.logw, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+  if (logWeights) {
+    if (d.logw) {
+      CK(cudaMemcpyAsync(logWeights, d.logw, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+      const double c0 = uniformLeafLogW(e);
+      for (int i = 0; i < N; ++i) logWeights[i] = c0;
+    }
+  }
   CK(cudaStreamSynchronize(e->stream));
   if (ancestors) {
     if (e->hStats[node].resampled) {
@@ -977,6 +1032,24 @@ int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre, i
       for (int i = 0; i < N; ++i) ancestors[i] = i;
     }
   }
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_debug_eval(dcsmc_engine* e, int32_t op, const double* x, double* y, int64_t n) {
+  if (!e) return DCSMC_EINVAL;
+  if (!x || !y || n < 0 || op < 0 || (op & 0xff) > 2) return e->fail(DCSMC_EINVAL, "dcsmc_debug_eval: bad arguments");
+  if (n == 0) return DCSMC_OK;
+  CK(cudaSetDevice(e->opt.device));
+  double *dx = nullptr, *dy = nullptr;
+  CK(cudaMalloc((void**)&dx, sizeof(double) * n));
+  CK(cudaMalloc((void**)&dy, sizeof(double) * n));
+  CK(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+  k_debug_eval<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(op, dx, dy, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(dx);
+  cudaFree(dy);
   return DCSMC_OK;
 }
 

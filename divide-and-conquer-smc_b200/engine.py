@@ -129,6 +129,12 @@ class Engine:
             self._h, node, _ptr(st, C.c_double), _ptr(ist, C.c_int32), _ptr(lw, C.c_double), _ptr(anc, C.c_int32)))
         return st, ist, lw, anc
 
+    def debug_eval(self, op: int, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self._ck(self._L.dcsmc_debug_eval(self._h, op, _ptr(x, C.c_double), _ptr(y, C.c_double), len(x)))
+        return y
+
     def packed_bytes(self) -> int:
         return int(self._L.dcsmc_population_packed_bytes(self._h))
 

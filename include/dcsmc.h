@@ -181,6 +181,10 @@ int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* sta
 int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre,
                               int32_t* istatePre, double* logWeights, int32_t* ancestors);
 
+/* Parity/debug: evaluate an elementary function of the numerics contract on the DEVICE for n host
+ * inputs (op 0: log, 1: exp — the fdlibm algorithms StrictMath specifies). */
+int32_t dcsmc_debug_eval(dcsmc_engine* e, int32_t op, const double* x, double* y, int64_t n);
+
 /* ---- moving populations between engines (replaces Hazelcast populations.put/remove,
  * DCRecursionTask.java:37,113) ---------------------------------------------------------- */
 
@@ -214,6 +218,8 @@ typedef struct dcsmc_run_info {
   int64_t nodesProcessed;
   int64_t algorithmicBytes; /* sum over nodes of N*(40*C + 184 [+16 multinomial]) */
   int64_t poolBytes;        /* device bytes reserved for populations */
+  int64_t h2dBytes;         /* host->device bytes copied by the last run call (tables, uniforms) */
+  int64_t d2hBytes;         /* device->host bytes copied by the last run call (node stats) */
   int32_t levelBatches;
   int32_t reserved;
 } dcsmc_run_info;

@@ -43,11 +43,12 @@ def compare_all(e, ref, csr, markov=False):
 
 @pytest.mark.parametrize("N", [1, 33, 1000, 5000])
 @pytest.mark.parametrize("threshold", [1.0 + 1e-10, 0.5])
-def test_multilevel_philox_stratified_bit_exact(N, threshold):
+@pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
+def test_multilevel_philox_bit_exact(N, threshold, scheme):
     csr, nT, nS = small_dataset()
-    ref = o.run(csr, N, masterRandomSeed=31, resamplingScheme=o.STRATIFIED, relativeEssThreshold=threshold,
+    ref = o.run(csr, N, masterRandomSeed=31, resamplingScheme=scheme, relativeEssThreshold=threshold,
                 rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
-    with Engine(nParticles=N, masterRandomSeed=31, resamplingScheme=1, relativeEssThreshold=threshold,
+    with Engine(nParticles=N, masterRandomSeed=31, resamplingScheme=scheme, relativeEssThreshold=threshold,
                 retainPopulations=1) as e:
         e.set_tree(csr)
         e.set_multilevel_model(nT, nS)
@@ -59,7 +60,9 @@ def test_multilevel_philox_stratified_bit_exact(N, threshold):
         assert np.array_equal(rw, ref.rootWeights)
 
 
-def test_multilevel_injected_stream_bit_exact():
+@pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
+@pytest.mark.parametrize("duplicates", [False, True])
+def test_multilevel_injected_stream_bit_exact(scheme, duplicates):
     """north_star: both sides driven by an identical injected uniform stream."""
     csr, nT, nS = small_dataset(seed=11)
     N, maxAtt = 777, 8
@@ -67,10 +70,14 @@ def test_multilevel_injected_stream_bit_exact():
     inj = []
     for n in range(csr.nNodes):
         S = o.slots_per_particle(csr, n, maxBetaAttempts=maxAtt)
-        inj.append(rng.random(N * S + N))
-    ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_INJECTED, sumMode=o.SUM_EXACT,
+        u = rng.random(N * S + N)
+        if duplicates:  # collisions: repeated and clustered darts (all in one sort bucket)
+            u[N * S + 10:N * S + 60] = u[N * S + 5]
+            u[N * S + 100:N * S + 300] = 0.5 + 1e-9 * rng.random(200)
+        inj.append(u)
+    ref = o.run(csr, N, resamplingScheme=scheme, rngMode=o.RNG_INJECTED, sumMode=o.SUM_EXACT,
                 elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, maxBetaAttempts=maxAtt, injected=inj, dump=True)
-    with Engine(nParticles=N, resamplingScheme=1, rngMode=1, maxBetaAttempts=maxAtt, retainPopulations=1) as e:
+    with Engine(nParticles=N, resamplingScheme=scheme, rngMode=1, maxBetaAttempts=maxAtt, retainPopulations=1) as e:
         e.set_tree(csr)
         e.set_multilevel_model(nT, nS)
         for n in range(csr.nNodes):
@@ -79,19 +86,20 @@ def test_multilevel_injected_stream_bit_exact():
         e.run()
         compare_all(e, ref, csr)
     # and the java-order / libm oracle (the most literal restatement of the Java) agrees within 1e-9
-    lit = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_INJECTED, sumMode=o.SUM_JAVA,
+    lit = o.run(csr, N, resamplingScheme=scheme, rngMode=o.RNG_INJECTED, sumMode=o.SUM_JAVA,
                 elemMode=o.ELEM_LIBM, nTrials=nT, nSuccesses=nS, maxBetaAttempts=maxAtt, injected=inj, dump=True)
     assert int((lit.anc != ref.anc).sum()) == 0
     assert np.allclose(lit.logNormEstimate, ref.logNormEstimate, rtol=1e-9, atol=0)
     assert np.allclose(lit.logw, ref.logw, rtol=1e-9, atol=1e-12)
 
 
-def test_markov_doc_model_philox_bit_exact():
+@pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
+def test_markov_doc_model_philox_bit_exact(scheme):
     csr = d.perfectBinaryTree(3).to_csr()
     N = 20000
-    ref = o.run(csr, N, model=o.MODEL_MARKOV, resamplingScheme=o.STRATIFIED, relativeEssThreshold=0.5,
+    ref = o.run(csr, N, model=o.MODEL_MARKOV, resamplingScheme=scheme, relativeEssThreshold=0.5,
                 rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, transition=T, prior=PRIOR, dump=True)
-    with Engine(nParticles=N, resamplingScheme=1, relativeEssThreshold=0.5, retainPopulations=1) as e:
+    with Engine(nParticles=N, resamplingScheme=scheme, relativeEssThreshold=0.5, retainPopulations=1) as e:
         e.set_tree(csr)
         e.set_markov_model(T, PRIOR)
         e.run()
@@ -99,13 +107,14 @@ def test_markov_doc_model_philox_bit_exact():
         assert abs(e.node_stats(0).logNormEstimate - (-3.600962588536195)) / 3.6 < 0.02
 
 
-def test_gauss_binary_tree_bit_exact():
+@pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
+def test_gauss_binary_tree_bit_exact(scheme):
     """BASELINE config 4 shape (small): perfect binary tree with observed real leaves."""
     csr, leafKind, leafObs = synth.binary_gauss_tree(5)
     N = 2000
-    ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+    ref = o.run(csr, N, resamplingScheme=scheme, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
                 elemMode=o.ELEM_FDLIBM, leafKind=leafKind, leafObs=leafObs, dump=True)
-    with Engine(nParticles=N, resamplingScheme=1, retainPopulations=1) as e:
+    with Engine(nParticles=N, resamplingScheme=scheme, retainPopulations=1) as e:
         e.set_tree(csr)
         e.set_multilevel_model(leafKind=leafKind, leafObs=leafObs)
         e.run()
@@ -144,3 +153,48 @@ def test_error_paths():
         bad[np.argmax(nT > 0)] = 10 ** 6  # nSuccesses > nTrials: logBinomialPr throws (DivideConquerMCAlgorithm.java:595)
         with pytest.raises(Exception):
             e.set_multilevel_model(nT, bad)
+
+
+@pytest.mark.parametrize("nTrials,nSucc", [(12, 0), (9, 9), (1, 1), (30, 11), (200, 3), (97, 60)])
+def test_beta_sampler_single_leaf_many_particles(nTrials, nSucc):
+    """Regression: the early-exit form of the Cheng BB/BC rejection loop was mis-compiled for
+    sm_100a (about 1 wrong draw in 3e4). A single-leaf tree with 2e5 particles exercises every
+    accept/reject path of both samplers; all draws must equal the oracle's."""
+    tree = d.DirectedTree(d.Node(("R",)))
+    csr = tree.to_csr()
+    nT = np.array([nTrials], np.int32)
+    nS = np.array([nSucc], np.int32)
+    N = 200_000
+    ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+    with Engine(nParticles=N, resamplingScheme=1, retainPopulations=1) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        state, _, lw, anc = e.debug_node(0)
+        assert np.array_equal(state, ref.state[0], equal_nan=True)
+        assert np.array_equal(anc, ref.anc[0])
+        assert e.node_stats(0).logNormEstimate == ref.logNormEstimate[0] == 0.0
+
+
+def test_device_elementary_functions_equal_fdlibm_oracle():
+    """dc_log / dc_exp on the device == the oracle's fdlibm restatement (StrictMath), bit for bit."""
+    L = o.lib()
+    rng = np.random.default_rng(5)
+    with Engine(nParticles=8) as e:
+        xs = np.concatenate([rng.uniform(-745, 709, 100000), rng.uniform(-2, 2, 100000), rng.normal(0, 1e-3, 20000),
+                             rng.normal(0, 1e-9, 20000),
+                             np.array([0.0, -0.0, 1e-300, 709.78, -745.13, -746, 710, np.inf, -np.inf, 0.34657359027997264,
+                                       -0.34657359027997264, 1.0397207708399179, -1.0397207708399179])])
+        yd = e.debug_eval(1, xs)
+        yo = np.array([L.orc_elem_exp(o.ELEM_FDLIBM, float(x)) for x in xs])
+        assert np.array_equal(yd, yo, equal_nan=True)
+        ys = np.concatenate([np.exp(rng.uniform(-700, 700, 100000)), rng.uniform(0.5, 2.0, 100000), rng.uniform(0, 1, 100000),
+                             1 + rng.normal(0, 1e-7, 20000), np.array([0.0, 1.0, 5e-324, 1e-310, 2.0, 0.5, np.inf, -1.0])])
+        yd = e.debug_eval(0, ys)
+        yo = np.array([L.orc_elem_log(o.ELEM_FDLIBM, float(x)) for x in ys])
+        assert np.array_equal(yd, yo, equal_nan=True)
+        idx = np.arange(0, 50000, dtype=np.float64)
+        ud = e.debug_eval(2 | (7 << 8), idx)
+        uo = np.array([L.orc_philox_uniform(31, 7, int(i)) for i in idx])
+        assert np.array_equal(ud, uo)
