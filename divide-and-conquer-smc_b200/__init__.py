@@ -13,3 +13,18 @@ from .tree import (  # noqa: F401
     java_string_hash,
     perfectBinaryTree,
 )
+from .dc import (  # noqa: F401,E402
+    DCOptions,
+    DCProcessor,
+    DCProcessorFactory,
+    DCProcessorFactoryContext,
+    DCProposalFactory,
+    DefaultProcessorFactory,
+    DistributedDC,
+    GaussianLeafProposalFactory,
+    MarkovChainNaiveProposalFactory,
+    MultiLevelProposalFactory,
+    NoOpProcessor,
+    ParticlePopulation,
+    ResamplingScheme,
+)

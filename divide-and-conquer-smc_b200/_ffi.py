@@ -74,7 +74,7 @@ SYMBOLS = [
     "dcsmc_run_nodes", "dcsmc_node_stats", "dcsmc_all_node_stats", "dcsmc_population_copy_to_host",
     "dcsmc_debug_copy_node", "dcsmc_population_packed_bytes", "dcsmc_population_pack",
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
-    "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval",
+    "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval", "dcsmc_reset_populations",
 ]
 
 _lib = None
@@ -116,6 +116,7 @@ def lib():
     L.dcsmc_population_pack.argtypes = [vp, i32, vp]
     L.dcsmc_population_unpack.argtypes = [vp, i32, vp]
     L.dcsmc_population_release.argtypes = [vp, i32]
+    L.dcsmc_reset_populations.argtypes = [vp]
     L.dcsmc_last_run_info.argtypes = [vp, P(RunInfo)]
     L.dcsmc_profile_enable.argtypes = [vp, i32]
     L.dcsmc_profile_get.argtypes = [vp, i32, P(dbl), P(i64)]

@@ -79,6 +79,7 @@ struct dcsmc_engine {
   size_t poolTop = 0;
   std::vector<Slot> slot;        // per node
   std::vector<char> resident;    // per node
+  std::vector<char> imported;    // per node: population installed by dcsmc_population_unpack
   std::vector<NodeDev> hNodes;   // host mirror
   std::vector<dcsmc_node_stats_t> hStats;
   int Npad = 0;
@@ -88,11 +89,8 @@ struct dcsmc_engine {
   size_t cdfCap = 0;
   unsigned long long* dDesc = nullptr;  // descA | descB | ticket
   size_t descCap = 0;
-  double* dDarts = nullptr;  // multinomial: bucket-ordered darts
-  size_t dartsCap = 0;
-  int32_t* dDartInts = nullptr;  // count | cursor | offset
-  size_t dartIntsCap = 0;
-  int NB = 1;
+  int32_t* dOffspring = nullptr;  // multinomial: offspring counts
+  size_t offspringCap = 0;
 
   // measurement
   dcsmc_run_info info{};
@@ -144,7 +142,7 @@ size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // bytes of one node's resident population. Leaves carry no log-weight column (all equal).
 size_t slotBytes(const dcsmc_engine* e, int n) {
   const size_t NP = (size_t)e->Npad;
-  const bool internal = nodeKind(e, n) == KIND_INTERNAL;
+  const bool internal = nodeKind(e, n) == KIND_INTERNAL || (!e->imported.empty() && e->imported[n]);
   size_t b = 0;
   if (e->model == DCSMC_MODEL_MARKOV) {
     b = NP * 4 /*istate*/ + NP * 4 /*anc*/ + (internal ? NP * 8 : 0) /*logw*/;
@@ -154,7 +152,10 @@ size_t slotBytes(const dcsmc_engine* e, int n) {
   return alignUp(b, 256);
 }
 
+void poolFree(dcsmc_engine* e, int n);
+
 bool poolAlloc(dcsmc_engine* e, int n) {
+  poolFree(e, n);  // recomputing a node reuses nothing of its old population
   const size_t b = slotBytes(e, n);
   auto it = e->freeBySize.find(b);
   size_t off;
@@ -185,6 +186,7 @@ void fillNodeDev(dcsmc_engine* e, int n) {
   d.nChildren = nChildrenOf(e, n);
   d.kind = nodeKind(e, n);
   d.pad = 0;
+  if (!e->imported.empty() && e->imported[n]) d.kind = KIND_INTERNAL;  // unpacked: 6 columns + logw
   const bool internal = d.kind == KIND_INTERNAL;
   if (e->model == DCSMC_MODEL_MARKOV) {
     d.state = nullptr;
@@ -285,6 +287,7 @@ int uploadTables(dcsmc_engine* e) {
   e->hStats.assign(nN, dcsmc_node_stats_t{});
   e->slot.assign(nN, Slot{});
   e->resident.assign(nN, 0);
+  e->imported.assign(nN, 0);
   e->freeBySize.clear();
   e->poolTop = 0;
   e->tablesDirty = false;
@@ -364,6 +367,7 @@ bool emitLevels(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan, bool
     st.offset = (int)plan.stepNodes.size();
     st.count = (int)lvl.size();
     for (int n : lvl) {
+      e->imported[n] = 0;
       if (!poolAlloc(e, n)) return false;
       peakTop = std::max(peakTop, e->poolTop);
       plan.stepNodes.push_back(n);
@@ -384,14 +388,17 @@ struct PoolState {
   std::multimap<size_t, size_t> freeBySize;
   size_t poolTop;
   std::vector<Slot> slot;
-  std::vector<char> resident;
+  std::vector<char> resident, imported;
 };
-PoolState savePool(const dcsmc_engine* e) { return PoolState{e->freeBySize, e->poolTop, e->slot, e->resident}; }
+PoolState savePool(const dcsmc_engine* e) {
+  return PoolState{e->freeBySize, e->poolTop, e->slot, e->resident, e->imported};
+}
 void restorePool(dcsmc_engine* e, const PoolState& s) {
   e->freeBySize = s.freeBySize;
   e->poolTop = s.poolTop;
   e->slot = s.slot;
   e->resident = s.resident;
+  e->imported = s.imported;
 }
 
 // Memory-aware recursive planner: try the whole root set level by level; if the pool
@@ -430,6 +437,7 @@ int planRoots(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan) {
   st.leaf = false;
   st.offset = (int)plan.stepNodes.size();
   st.count = 1;
+  e->imported[r] = 0;
   if (!poolAlloc(e, r))
     return e->fail(DCSMC_ENOMEM, "population pool (%zu bytes) too small for node %d and its children",
                    e->poolBytes, r);
@@ -519,26 +527,22 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
     ProfScope p(e, DCSMC_K_RESAMPLE);
     k_resample_stratified<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
   } else {
-    const size_t nb = (size_t)st.count * c.NB;
-    c.dartCount = e->dDartInts;
-    c.dartCursor = e->dDartInts + nb;
-    c.dartOffset = e->dDartInts + 2 * nb;
-    CK(cudaMemsetAsync(e->dDartInts, 0, 2 * nb * sizeof(int32_t), e->stream));
+    // multinomial: offspring counts by atomics, then scan + expansion (no dart sort)
+    const int tilesE = (N + EXPAND_TILE - 1) / EXPAND_TILE;
+    const size_t needDescE = (size_t)st.count * tilesE;
+    c.offspring = e->dOffspring;
+    c.descA = e->dDesc;
+    c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + needDescE);
+    CK(cudaMemsetAsync(e->dOffspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), e->stream));
     {
       ProfScope p(e, DCSMC_K_DARTS);
-      k_darts_hist<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+      k_darts_count<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
     }
-    {
-      ProfScope p(e, DCSMC_K_DARTS);
-      k_darts_scan<<<st.count, 256, 0, e->stream>>>(c);
-    }
-    {
-      ProfScope p(e, DCSMC_K_DARTS);
-      k_darts_scatter<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
-    }
+    // the look-back descriptors of the scan are dead by now (stream order): reuse them
+    CK(cudaMemsetAsync(e->dDesc, 0, (needDescE + 1) * sizeof(unsigned long long), e->stream));
     {
       ProfScope p(e, DCSMC_K_RESAMPLE);
-      k_resample_multinomial<<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+      k_expand<<<(unsigned)(st.count * tilesE), EXPAND_THREADS, 0, e->stream>>>(c, tilesE);
     }
   }
   CK(cudaGetLastError());
@@ -570,8 +574,6 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.dN = (double)N;
   c.threshold = e->opt.relativeEssThreshold;
   c.cdf = e->dCdf;
-  c.darts = e->dDarts;
-  c.NB = e->NB;
   c.uniformLogW = uniformLeafLogW(e);
   return DCSMC_OK;
 }
@@ -613,13 +615,14 @@ int executePlan(dcsmc_engine* e, Plan& plan) {
     return r;
   };
   CK(grow((void**)&e->dCdf, e->cdfCap, std::max<size_t>(1, maxInternalStep * (size_t)e->Npad), sizeof(double)));
-  CK(grow((void**)&e->dDesc, e->descCap, 2 * maxInternalStep * tilesS + 1, sizeof(unsigned long long)));
-  e->NB = 1;
-  while ((size_t)e->NB * 16 < (size_t)N) e->NB <<= 1;
-  if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL) {
-    CK(grow((void**)&e->dDarts, e->dartsCap, maxStep * (size_t)e->Npad, sizeof(double)));
-    CK(grow((void**)&e->dDartInts, e->dartIntsCap, maxStep * (3 * (size_t)e->NB + 1), sizeof(int32_t)));
+  {
+    const size_t tilesE = (N + EXPAND_TILE - 1) / EXPAND_TILE;
+    size_t needDesc = 2 * maxInternalStep * tilesS + 1;
+    if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL) needDesc = std::max(needDesc, maxStep * tilesE + 1);
+    CK(grow((void**)&e->dDesc, e->descCap, needDesc, sizeof(unsigned long long)));
   }
+  if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL)
+    CK(grow((void**)&e->dOffspring, e->offspringCap, maxStep * (size_t)e->Npad, sizeof(int32_t)));
   if (plan.stepNodes.size() > e->stepNodesCap) {
     if (e->dStepNodes) cudaFree(e->dStepNodes);
     e->dStepNodes = nullptr;
@@ -788,7 +791,7 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   for (double* p : e->injDev)
     if (p) cudaFree(p);
   void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dInj, e->dJavaState,
-                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dDarts, e->dDartInts};
+                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -919,9 +922,7 @@ int32_t dcsmc_run(dcsmc_engine* e) {
   if (!e) return DCSMC_EINVAL;
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
   // a fresh run recomputes everything
-  std::fill(e->resident.begin(), e->resident.end(), 0);
-  e->freeBySize.clear();
-  e->poolTop = 0;
+  dcsmc_reset_populations(e);
   return runRoots(e, std::vector<int>{e->root});
 }
 
@@ -1056,17 +1057,69 @@ int32_t dcsmc_debug_eval(dcsmc_engine* e, int32_t op, const double* x, double* y
 int64_t dcsmc_population_packed_bytes(const dcsmc_engine* e) {
   if (!e) return 0;
   const size_t NP = alignUp((size_t)e->opt.nParticles, 32);
-  return (int64_t)(256 + NP * 8 * 7 + NP * 4);
+  return (int64_t)(sizeof(PackedHeader) + NP * 8 * 7 + NP * 4);
 }
 
-int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t, void*) {
+int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t node, void* deviceDst) {
   if (!e) return DCSMC_EINVAL;
-  return e->fail(DCSMC_EINVAL, "dcsmc_population_pack: not implemented yet");
+  if (node < 0 || node >= e->nNodes || !deviceDst) return e->fail(DCSMC_EINVAL, "dcsmc_population_pack: bad arguments");
+  if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+    return e->fail(DCSMC_ESTATE, "population of node %d is not resident", node);
+  CK(cudaSetDevice(e->opt.device));
+  RunCtx c;
+  makeCtx(e, c);
+  const int N = e->opt.nParticles;
+  e->info.kernelLaunches++;
+  k_pack<<<(N + 255) / 256, 256, 0, e->stream>>>(c, node, static_cast<char*>(deviceDst));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return DCSMC_OK;
 }
-int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t, const void*) {
+
+int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* deviceSrc) {
   if (!e) return DCSMC_EINVAL;
-  return e->fail(DCSMC_EINVAL, "dcsmc_population_unpack: not implemented yet");
+  if (node < 0 || node >= e->nNodes || !deviceSrc) return e->fail(DCSMC_EINVAL, "dcsmc_population_unpack: bad arguments");
+  int rc;
+  if ((rc = prepare(e))) return rc;
+  PackedHeader h;
+  CK(cudaMemcpy(&h, deviceSrc, sizeof h, cudaMemcpyDeviceToHost));
+  if (h.magic != PACK_MAGIC || h.N != e->opt.nParticles || h.model != (e->model == DCSMC_MODEL_MARKOV ? 1 : 0))
+    return e->fail(DCSMC_EINVAL, "packed population does not match this engine (magic/N/model)");
+  poolFree(e, node);
+  e->imported[node] = 1;
+  if (!poolAlloc(e, node)) {
+    e->imported[node] = 0;
+    return e->fail(DCSMC_ENOMEM, "population pool (%zu bytes) cannot hold the unpacked node %d", e->poolBytes, node);
+  }
+  fillNodeDev(e, node);
+  CK(cudaMemcpyAsync(e->dNodes + node, &e->hNodes[node], sizeof(NodeDev), cudaMemcpyHostToDevice, e->stream));
+  RunCtx c;
+  makeCtx(e, c);
+  const int N = e->opt.nParticles;
+  e->info.kernelLaunches++;
+  k_unpack<<<(N + 255) / 256, 256, 0, e->stream>>>(c, node, static_cast<const char*>(deviceSrc));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  dcsmc_node_stats_t& o = e->hStats[node];
+  o.ess = h.ess;
+  o.relEss = h.relEss;
+  o.logNormEstimate = h.logZ;
+  o.logScaling = h.logScaling;
+  o.resampled = h.resampled;
+  o.done = 1;
+  return DCSMC_OK;
 }
+
+int32_t dcsmc_reset_populations(dcsmc_engine* e) {
+  if (!e) return DCSMC_EINVAL;
+  std::fill(e->resident.begin(), e->resident.end(), 0);
+  std::fill(e->imported.begin(), e->imported.end(), 0);
+  for (auto& s : e->hStats) s = dcsmc_node_stats_t{};
+  e->freeBySize.clear();
+  e->poolTop = 0;
+  return DCSMC_OK;
+}
+
 int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node) {
   if (!e) return DCSMC_EINVAL;
   if (node < 0 || node >= e->nNodes || e->resident.empty()) return e->fail(DCSMC_EINVAL, "bad node %d", node);

@@ -1,0 +1,464 @@
+"""Host-side mirror of the reference's `dc` package (the plugin surface a user of the reference
+programs against), driving the CUDA engine through the C ABI.
+
+Mirrors (paths relative to /root/reference/src/main/java):
+  dc/DCOptions.java:15-45                -> DCOptions (same field names and defaults)
+  bayonet.smc.ResamplingScheme           -> ResamplingScheme
+  bayonet.smc.ParticlePopulation         -> ParticlePopulation (accessors of SURVEY §8a row P)
+  dc/DCProposalFactory.java:15-26        -> DCProposalFactory (GPU proposal *families*)
+  prototype/adaptor/MultiLevelProposalFactory.java -> MultiLevelProposalFactory
+  src/test/java/dc/Doc.java:206-225      -> MarkovChainNaiveProposalFactory
+  dc/DCProcessor*.java, DefaultProcessorFactory.java -> DCProcessor, DCProcessorFactory, DefaultProcessorFactory
+  dc/DistributedDC.java:58-107           -> DistributedDC (createInstance/addProcessorFactory/start/getRootPopulation)
+
+A per-particle Python callback cannot run on the GPU, so a DCProposalFactory here names a proposal
+family implemented by the kernels; `build(random, node, children)` keeps its meaning (leaf vs
+internal proposal of that family).
+"""
+from __future__ import annotations
+
+import enum
+import os
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi as F
+from . import sharding
+from .engine import Engine
+from .tree import CsrTree, DirectedTree, MultiLevelDataset, Node
+
+THRESHOLD = 1e-10  # stands in for bayonet NumericalUtils.THRESHOLD (any rESS <= 1 is below 1+THRESHOLD)
+
+
+class ResamplingScheme(enum.IntEnum):
+    MULTINOMIAL = 0
+    STRATIFIED = 1
+
+
+@dataclass
+class DCOptions:
+    """dc/DCOptions.java:15-45, field for field."""
+
+    masterRandomSeed: int = 31
+    nParticles: int = 1000
+    resamplingScheme: ResamplingScheme = ResamplingScheme.MULTINOMIAL
+    relativeEssThreshold: float = 1.0 + THRESHOLD
+    clusterSubGroup: int = 1
+    nThreadsPerNode: int = 1
+    minimumNumberOfClusterMembersToStart: int = 1
+    maximumTimeToWaitInMinutes: int = 1
+    maximumDistributionDepth: int = 2 ** 31 - 1
+    indexInCluster: int = 1
+    # engine extensions
+    rngMode: int = F.RNG_PHILOX
+    maxBetaAttempts: int = 32
+    retainPopulations: bool = False
+    memoryBudgetBytes: int = 0
+
+    def engine_kwargs(self, device: int = 0) -> Dict[str, Any]:
+        return dict(
+            masterRandomSeed=int(self.masterRandomSeed), nParticles=int(self.nParticles),
+            resamplingScheme=int(self.resamplingScheme), relativeEssThreshold=float(self.relativeEssThreshold),
+            clusterSubGroup=self.clusterSubGroup, nThreadsPerNode=self.nThreadsPerNode,
+            minimumNumberOfClusterMembersToStart=self.minimumNumberOfClusterMembersToStart,
+            maximumTimeToWaitInMinutes=self.maximumTimeToWaitInMinutes,
+            maximumDistributionDepth=int(min(self.maximumDistributionDepth, 2 ** 31 - 1)),
+            indexInCluster=self.indexInCluster, device=device, rngMode=self.rngMode,
+            maxBetaAttempts=self.maxBetaAttempts, retainPopulations=1 if self.retainPopulations else 0,
+            memoryBudgetBytes=self.memoryBudgetBytes)
+
+
+class ParticlePopulation:
+    """bayonet.smc.ParticlePopulation as the reference uses it (DCRecursion.java:29-31,58-59,70,73;
+    DefaultProcessorFactory.java:45-47): particles, normalised weights (None => all equal),
+    logScaling. Particles stay on the GPU; `particles` is a host copy made on first access."""
+
+    def __init__(self, n: int, logScaling: float, ess: float, weights_null: bool, fetch=None):
+        self._n = n
+        self.logScaling = logScaling
+        self._ess = ess
+        self._weights_null = weights_null
+        self._fetch = fetch
+        self._particles = None
+        self._weights = None
+
+    def nParticles(self) -> int:
+        return self._n
+
+    def _load(self):
+        if self._particles is None:
+            if self._fetch is None:
+                raise RuntimeError("this population's particles were consumed by its parent (DCRecursionTask.java:113)")
+            self._particles, self._weights = self._fetch()
+
+    @property
+    def particles(self):
+        self._load()
+        return self._particles
+
+    def getNormalizedWeight(self, index: int) -> float:
+        if self._weights_null:
+            return 1.0 / self._n
+        self._load()
+        return float(self._weights[index])
+
+    def getESS(self) -> float:
+        return self._ess
+
+    def getRelativeESS(self) -> float:
+        return self._ess / self._n
+
+    def logNormEstimate(self) -> float:
+        # logScaling - log N
+        return self.logScaling - float(np.log(self._n))
+
+
+# ---- proposal families ------------------------------------------------------------------------------
+
+class DCProposalFactory:
+    """dc/DCProposalFactory.java:15-26. configure() installs the family on an engine."""
+
+    def configure(self, engine: Engine, csr: CsrTree):
+        raise NotImplementedError
+
+    def build(self, random, currentNode, childrenNodes):
+        return ("leaf" if len(childrenNodes) == 0 else "internal", currentNode)
+
+
+class MultiLevelProposalFactory(DCProposalFactory):
+    """prototype/adaptor/MultiLevelProposalFactory.java:20-52 (options dataFile, variancePrior)."""
+
+    def __init__(self, dataFile: Optional[str] = None, variancePrior: float = 1.0, dataset: Optional[MultiLevelDataset] = None):
+        self.dataFile = dataFile
+        self.variancePrior = variancePrior
+        self._dataset = dataset
+
+    def getDataset(self) -> MultiLevelDataset:
+        if self._dataset is None:
+            if self.dataFile is None:
+                raise RuntimeError("dataFile is required")  # @Option(required = true)
+            self._dataset = MultiLevelDataset(self.dataFile)
+        return self._dataset
+
+    def configure(self, engine: Engine, csr: CsrTree):
+        nT, nS = self.getDataset().leaf_arrays(csr)
+        engine.set_multilevel_model(nT, nS, None, None, self.variancePrior)
+
+
+class GaussianLeafProposalFactory(DCProposalFactory):
+    """BASELINE config 4: internal nodes as MultiLevelInternalProposal, leaves are observed reals
+    (BrownianModelCalculator.observation)."""
+
+    def __init__(self, leafObs: Dict[Any, float], variancePrior: float = 1.0):
+        self.leafObs = leafObs
+        self.variancePrior = variancePrior
+
+    def configure(self, engine: Engine, csr: CsrTree):
+        obs = np.zeros(csr.nNodes)
+        kind = np.zeros(csr.nNodes, np.int32)
+        for i, n in enumerate(csr.nodes):
+            if csr.nChildren(i) == 0:
+                obs[i] = self.leafObs[n]
+                kind[i] = F.LEAF_GAUSS_OBS
+        engine.set_multilevel_model(None, None, kind, obs, self.variancePrior)
+
+
+class MarkovChainNaiveProposalFactory(DCProposalFactory):
+    """Doc.markovChainNaiveProposalFactory (src/test/java/dc/Doc.java:206-225)."""
+
+    def __init__(self, transition, prior):
+        self.transition = np.asarray(transition, dtype=np.float64)
+        self.prior = np.asarray(prior, dtype=np.float64).reshape(-1)
+        n = self.transition.shape[0]
+        # TestUtilities.checkValidMarkovChain (TestUtilities.java:76-82)
+        if self.transition.shape != (n, n) or self.prior.shape != (n,):
+            raise RuntimeError()
+
+    def configure(self, engine: Engine, csr: CsrTree):
+        engine.set_markov_model(self.transition, self.prior)
+
+
+# ---- processors ---------------------------------------------------------------------------------------
+
+class DCProcessor:
+    """dc/DCProcessor.java:16-22"""
+
+    def process(self, populationBeforeResampling: ParticlePopulation, childrenPopulations: List[ParticlePopulation]):
+        pass
+
+
+@dataclass
+class DCProcessorFactoryContext:
+    """dc/DCProcessorFactoryContext.java:7-16"""
+
+    currentNode: Any
+    _tree: DirectedTree
+    dc: "DistributedDC"
+
+    def tree(self) -> DirectedTree:
+        return self._tree
+
+
+class DCProcessorFactory:
+    """dc/DCProcessorFactory.java:13-21"""
+
+    def build(self, context: DCProcessorFactoryContext) -> DCProcessor:
+        return DCProcessor()
+
+    def close(self):
+        pass
+
+
+class NoOpProcessor(DCProcessor):
+    """dc/NoOpProcessor.java"""
+
+
+class DefaultProcessorFactory(DCProcessorFactory):
+    """dc/DefaultProcessorFactory.java:15-64: one `timing` row per node (node, ESS, rESS, logZ,
+    nWorkers, iterationProposalTime, globalTime), the root's logZ in file `logZ`, total time in
+    `workTime`. Rows are kept in memory and written as CSV when a results folder is given."""
+
+    def __init__(self, resultsFolder: Optional[str] = None, echo: bool = False):
+        self.rows: List[Dict[str, Any]] = []
+        self.resultsFolder = resultsFolder
+        self.echo = echo
+        self._t0 = None
+        self.logZ = None
+
+    def build(self, context: DCProcessorFactoryContext) -> DCProcessor:
+        if self._t0 is None:
+            self._t0 = time.perf_counter()
+        factory = self
+
+        class _P(DCProcessor):
+            def process(self, pop, children):
+                row = dict(node=str(context.currentNode), ESS=pop.getESS(), rESS=pop.getRelativeESS(),
+                           logZ=pop.logNormEstimate(), nWorkers=context.dc.nWorkers,
+                           iterationProposalTime=context.dc.nodeTimeMs.get(context.currentNode, 0.0),
+                           globalTime=context.dc.globalTimeMs)
+                factory.rows.append(row)
+                if factory.echo:
+                    print("timing: " + ", ".join(f"{k}={v}" for k, v in row.items()))
+                if context.tree().getRoot() == context.currentNode:
+                    factory.logZ = pop.logNormEstimate()
+
+        return _P()
+
+    def close(self):
+        if self.resultsFolder:
+            os.makedirs(self.resultsFolder, exist_ok=True)
+            with open(os.path.join(self.resultsFolder, "timing.csv"), "w") as fh:
+                cols = ["node", "ESS", "rESS", "logZ", "nWorkers", "iterationProposalTime", "globalTime"]
+                fh.write(",".join(cols) + "\n")
+                for r in self.rows:
+                    fh.write(",".join(str(r[c]) for c in cols) + "\n")
+            if self.logZ is not None:
+                with open(os.path.join(self.resultsFolder, "logZ"), "w") as fh:
+                    fh.write(str(self.logZ))
+            with open(os.path.join(self.resultsFolder, "workTime"), "w") as fh:
+                fh.write(str(self.rows[-1]["globalTime"] if self.rows else 0))
+
+
+# ---- orchestration ---------------------------------------------------------------------------------------
+
+class DistributedDC:
+    """dc/DistributedDC.java. createInstance / addProcessorFactory / start / getRootPopulation keep
+    their contracts; Hazelcast is replaced by static subtree sharding over the ranks of
+    torch.distributed (one process per GPU) when a process group is initialised."""
+
+    def __init__(self, options: DCOptions, proposalFactory: DCProposalFactory, tree: DirectedTree, device: Optional[int] = None):
+        self.options = options
+        self.proposalFactory = proposalFactory
+        self.tree = tree
+        self.processorFactories: List[DCProcessorFactory] = [DefaultProcessorFactory()]
+        self._started = False
+        self._rootPopulation: Optional[ParticlePopulation] = None
+        self.csr = tree.to_csr()
+        self.device = device
+        self.engine: Optional[Engine] = None
+        self.stats: Optional[Dict[str, np.ndarray]] = None
+        self.nWorkers = 1
+        self.nodeTimeMs: Dict[Any, float] = {}
+        self.globalTimeMs = 0.0
+        self.lastRun: Dict[str, Any] = {}
+
+    @staticmethod
+    def createInstance(options: DCOptions, proposalFactory: DCProposalFactory, tree: DirectedTree, device: Optional[int] = None) -> "DistributedDC":
+        # the reference allows one instance per JVM (DistributedDC.java:63-67); engines are independent here
+        return DistributedDC(options, proposalFactory, tree, device)
+
+    def addProcessorFactory(self, factory: DCProcessorFactory):
+        self.processorFactories.append(factory)
+
+    # -- execution --------------------------------------------------------------------------------------
+    def _dist(self):
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                return dist
+        except Exception:
+            pass
+        return None
+
+    engineFactory = None  # tests inject a CPU stand-in for the host-side plumbing
+
+    def _make_engine(self):
+        if self.engineFactory is not None:
+            return self.engineFactory(self)
+        dev = self.device
+        if dev is None:
+            dev = int(os.environ.get("LOCAL_RANK", "0"))
+        e = Engine(**self.options.engine_kwargs(dev))
+        e.set_tree(self.csr)
+        self.proposalFactory.configure(e, self.csr)
+        return e
+
+    def start(self):
+        if self._started:  # checkNotAlreadyStarted, DistributedDC.java:177-182
+            raise RuntimeError()
+        self._started = True
+        self.run()
+        self._finish()
+
+    def run(self):
+        """One execution of the whole tree (start() without the start-once guard; used by bench.py)."""
+        if self.engine is None:
+            self.engine = self._make_engine()
+        dist = self._dist()
+        t0 = time.perf_counter()
+        if dist is None:
+            self.engine.run()
+            self.stats = self.engine.all_node_stats()
+            info = self.engine.run_info()
+            self.lastRun = dict(deviceMs=info.deviceMs, kernelLaunches=info.kernelLaunches,
+                                particleUpdates=info.particleUpdates, algorithmicBytes=info.algorithmicBytes,
+                                h2dBytes=info.h2dBytes, d2hBytes=info.d2hBytes, nvlinkBytes=0)
+            self.rootOwner = 0
+        else:
+            self._run_sharded(dist)
+        self.globalTimeMs = (time.perf_counter() - t0) * 1e3
+
+    def _run_sharded(self, dist):
+        import torch
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        self.nWorkers = world
+        e = self.engine
+        plan = sharding.make_plan(self.csr, self.options.maximumDistributionDepth, world)
+        self.plan = plan
+        e.reset_populations()
+        dev = torch.device("cuda", e.options.device) if torch.cuda.is_available() else torch.device("cpu")
+        nbytes = e.packed_bytes()
+        launches = updates = algbytes = nvbytes = 0
+        devms = 0.0
+
+        def account():
+            nonlocal launches, updates, algbytes, devms
+            info = e.run_info()
+            launches += info.kernelLaunches
+            updates += info.particleUpdates
+            algbytes += info.algorithmicBytes
+            devms += info.deviceMs
+
+        mine = plan.my_tasks(rank)
+        if mine:
+            e.run_subtrees(mine)
+            account()
+        for lvl in plan.top_levels:
+            ops, recvs, sends = [], [], []
+            for child, src, dst in lvl.transfers:
+                if rank == src:
+                    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    e.pack(child, buf.data_ptr())
+                    launches += 1
+                    sends.append((child, buf))
+                    ops.append(dist.P2POp(dist.isend, buf, dst))
+                elif rank == dst:
+                    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    recvs.append((child, buf))
+                    ops.append(dist.P2POp(dist.irecv, buf, src))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                if dev.type == "cuda":
+                    torch.cuda.current_stream(dev).synchronize()
+            for child, buf in sends:
+                e.release(child)
+                nvbytes += nbytes
+            for child, buf in recvs:
+                e.unpack(child, buf.data_ptr())
+                launches += 1
+            my_nodes = [n for n, own in lvl.nodes if own == rank]
+            if my_nodes:
+                e.run_nodes(my_nodes)
+                account()
+        # every rank learns every node's statistics (each node was computed on exactly one rank)
+        st = e.all_node_stats()
+        own = np.array([plan.node_owner.get(n, -1) for n in range(self.csr.nNodes)])
+        # nodes strictly inside a task subtree belong to the task's owner
+        for t in plan.tasks:
+            stack = [t]
+            while stack:
+                n = stack.pop()
+                own[n] = plan.task_owner[t]
+                stack.extend(int(c) for c in self.csr.children[self.csr.childOffsets[n]:self.csr.childOffsets[n + 1]])
+        keys = ["ess", "relEss", "logNormEstimate", "logScaling"]
+        mat = np.stack([np.where(own == rank, st[k], 0.0) for k in keys] + [np.where(own == rank, st["resampled"], 0).astype(np.float64)])
+        tens = torch.from_numpy(mat).to(dev)
+        dist.all_reduce(tens)
+        mat = tens.cpu().numpy()
+        self.stats = {k: mat[i] for i, k in enumerate(keys)}
+        self.stats["resampled"] = mat[4].astype(np.int32)
+        self.stats["done"] = np.ones(self.csr.nNodes, np.int32)
+        self.rootOwner = plan.node_owner[0]
+        self.lastRun = dict(deviceMs=devms, kernelLaunches=launches, particleUpdates=updates, algorithmicBytes=algbytes,
+                            h2dBytes=0, d2hBytes=0, nvlinkBytes=nvbytes)
+
+    def _population_view(self, i: int, fetch=None) -> ParticlePopulation:
+        st = self.stats
+        return ParticlePopulation(self.options.nParticles, float(st["logScaling"][i]), float(st["ess"][i]),
+                                  weights_null=False, fetch=fetch)
+
+    def _finish(self):
+        # DCProcessor.process sees the population BEFORE resampling (DCRecursion.java:27-28)
+        csr = self.csr
+        procs = []
+        for i, node in enumerate(csr.nodes):
+            ctx = DCProcessorFactoryContext(node, self.tree, self)
+            procs.append([f.build(ctx) for f in self.processorFactories])
+        h = csr.height()
+        order = sorted(range(csr.nNodes), key=lambda i: (int(h[i]), i))
+        for i in order:
+            pop = self._population_view(i)
+            kids = [self._population_view(int(c)) for c in csr.children[csr.childOffsets[i]:csr.childOffsets[i + 1]]]
+            for p in procs[i]:
+                p.process(pop, kids)
+        for f in self.processorFactories:
+            f.close()
+        # root population, saved locally for convenience (DistributedDC.java:101-102)
+        st = self.stats
+        resampled = bool(st["resampled"][0])
+        eng = self.engine
+        dist = self._dist()
+        can_fetch = dist is None or dist.get_rank() == self.rootOwner
+        markov = isinstance(self.proposalFactory, MarkovChainNaiveProposalFactory)
+
+        def fetch():
+            state, istate, w = eng.population(0, state=not markov, istate=markov, weights=True)
+            return (istate if markov else state), w
+
+        self._rootPopulation = ParticlePopulation(self.options.nParticles, float(st["logScaling"][0]), float(st["ess"][0]),
+                                                  weights_null=resampled, fetch=fetch if can_fetch else None)
+        if resampled:
+            self._rootPopulation._ess = float(self.options.nParticles)  # equally weighted after resample()
+
+    def getRootPopulation(self) -> ParticlePopulation:
+        return self._rootPopulation
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None

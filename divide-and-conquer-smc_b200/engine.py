@@ -144,6 +144,9 @@ class Engine:
     def unpack(self, node: int, device_ptr: int):
         self._ck(self._L.dcsmc_population_unpack(self._h, node, C.c_void_p(device_ptr)))
 
+    def reset_populations(self):
+        self._ck(self._L.dcsmc_reset_populations(self._h))
+
     def release(self, node: int):
         self._ck(self._L.dcsmc_population_release(self._h, node))
 

@@ -196,6 +196,9 @@ int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t node, void* deviceDst);
 int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* deviceSrc);
 /* release a node's population (the parent consumed it) */
 int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node);
+/* forget every resident population and statistic (dcsmc_run does this itself; callers of
+ * dcsmc_run_subtrees / dcsmc_run_nodes use it between independent executions) */
+int32_t dcsmc_reset_populations(dcsmc_engine* e);
 
 /* ---- measurement ---------------------------------------------------------------------- */
 

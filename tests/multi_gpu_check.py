@@ -1,0 +1,64 @@
+"""torchrun script: the sharded multi-GPU run must give bit-identical node statistics and root
+population to a single-GPU run and to the oracle (per-node streams keyed by node id, Doc.java:268)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import dcsmc_b200 as d
+from dcsmc_b200 import synth
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rows = synth.wide_rows(5, [3, 4, 3])
+    ds = d.MultiLevelDataset(rows=rows)
+    N = 20000
+    for scheme in (d.ResamplingScheme.MULTINOMIAL, d.ResamplingScheme.STRATIFIED):
+        for thr in (1.0 + 1e-10, 0.6):
+            for depth in (1, 2, 2 ** 31 - 1):
+                opt = d.DCOptions(nParticles=N, resamplingScheme=scheme, relativeEssThreshold=thr, maximumDistributionDepth=depth)
+                ddc = d.DistributedDC.createInstance(opt, d.MultiLevelProposalFactory(dataset=ds), ds.getTree(), device=local)
+                ddc.start()
+                sharded = {k: v.copy() for k, v in ddc.stats.items()}
+                moved = ddc.lastRun["nvlinkBytes"]
+                root = None
+                if rank == ddc.rootOwner:
+                    root = ddc.getRootPopulation().particles.copy()
+                # single-GPU run on every rank (no process group use): engine.run()
+                ddc.engine.run()
+                single = ddc.engine.all_node_stats()
+                for k in ("ess", "relEss", "logNormEstimate", "logScaling", "resampled"):
+                    assert np.array_equal(sharded[k], single[k]), (scheme, thr, depth, k)
+                if root is not None:
+                    s, _, _ = ddc.engine.population(0)
+                    assert np.array_equal(root, s, equal_nan=True)
+                tot = torch.tensor([moved], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tot)
+                assert tot.item() > 0, "nothing crossed NVLink"
+                ddc.close()
+    if rank == 0:
+        import oracle_lib as o
+
+        csr = ds.getTree().to_csr()
+        nT, nS = ds.leaf_arrays(csr)
+        ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, relativeEssThreshold=0.6, rngMode=o.RNG_PHILOX,
+                    sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
+        assert np.array_equal(ref.logNormEstimate, sharded["logNormEstimate"])
+        print("MULTI_GPU_CHECK_OK world", world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,259 @@
+"""CPU tests of the host side: C-ABI library loading/exports, topology + dataset mirror,
+sharding plan, and the multi-rank plumbing over gloo (world_size 2) with a CPU stand-in engine."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import dcsmc_b200 as d
+from dcsmc_b200 import _ffi, sharding, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _ffi.lib()
+    hdr = open(os.path.join(ROOT, "include", "dcsmc.h")).read()
+    declared = set(re.findall(r"\b(dcsmc_[a-z_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/dcsmc.h but not exported"
+    assert declared == set(_ffi.SYMBOLS)
+    assert L.dcsmc_abi_version() == 1
+
+
+def test_options_default_mirror_dcoptions():
+    L = _ffi.lib()
+    o = _ffi.Options()
+    assert L.dcsmc_options_default(C.byref(o)) == 0
+    ref = d.DCOptions()
+    assert o.masterRandomSeed == ref.masterRandomSeed == 31            # DCOptions.java:16
+    assert o.nParticles == ref.nParticles == 1000                      # :19
+    assert o.resamplingScheme == int(ref.resamplingScheme) == 0        # :22 MULTINOMIAL
+    assert o.relativeEssThreshold > 1.0 and ref.relativeEssThreshold > 1.0  # :25 always resample
+    assert o.nThreadsPerNode == 1 and o.maximumDistributionDepth == 2 ** 31 - 1  # :32,:41
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dcsmc_b200.engine import Engine
+
+    with pytest.raises(_ffi.DcsmcError) as ei:
+        Engine(nParticles=10)
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_create_argument_validation():
+    L = _ffi.lib()
+    o = _ffi.Options()
+    L.dcsmc_options_default(C.byref(o))
+    h = C.c_void_p()
+    o.nParticles = 0
+    assert L.dcsmc_create(C.byref(o), C.byref(h)) == _ffi.EINVAL
+    o.nParticles = 1 << 24
+    assert L.dcsmc_create(C.byref(o), C.byref(h)) == _ffi.EINVAL
+    assert b"nParticles" in L.dcsmc_last_error(None)
+
+
+def test_dataset_first_appearance_order_and_tree(tmp_path):
+    rows = [["R", "b", "x", "10", "3"], ["R", "a", "y", "5", "5"], ["R", "b", "z", "7", "0"], ["R", "a", "y2", "4", "1"]]
+    p = tmp_path / "data.csv"
+    synth.write_csv(rows, str(p))
+    ds = d.MultiLevelDataset(str(p))
+    assert ds.getRoot() == d.Node(("R",))
+    # MultiLevelDataset.java:24,61-62: children in first-appearance order
+    assert [n.toString() for n in ds.getChildren(ds.getRoot())] == ["R-b", "R-a"]
+    assert [n.toString() for n in ds.getChildren(d.Node(("R", "b")))] == ["R-b-x", "R-b-z"]
+    assert ds.getDatum(d.Node(("R", "a", "y"))).numberOfTrials == 5
+    csr = ds.getTree().to_csr()
+    assert csr.nNodes == 7 and csr.nChildren(0) == 2
+    nT, nS = ds.leaf_arrays(csr)
+    assert nT[csr.index[d.Node(("R", "b", "z"))]] == 7 and nS[csr.index[d.Node(("R", "a", "y"))]] == 5
+    assert [n.toString() for n in ds.postOrder()][-1] == "R"
+    assert d.Node(("R", "b")).level() == 1
+
+
+def test_nys_shaped_generator_shape():
+    rows = synth.nys_shaped_rows()
+    ds = d.MultiLevelDataset(rows=rows)
+    csr = ds.getTree().to_csr()
+    assert list(np.bincount(csr.depth())) == [1, 5, 32, 700, 2800]
+    assert all(0 <= int(r[-1]) <= int(r[-2]) for r in rows)
+
+
+def test_perfect_binary_tree_labels():
+    t = d.perfectBinaryTree(3)
+    csr = t.to_csr()
+    assert csr.nNodes == 15
+    assert [n.toString() for n in t.getChildren(t.getRoot())] == ["0-0", "0-1"]  # TestUtilities.java:22,34
+
+
+def test_initial_tasks_match_reference_recursion():
+    csr = d.perfectBinaryTree(4).to_csr()
+    # DistributedDC.populateInitialTasks: depth 0 -> root only; depth 2 -> the 4 depth-2 nodes
+    assert sharding.initial_tasks(csr, 0) == [0]
+    depth = csr.depth()
+    t2 = sharding.initial_tasks(csr, 2)
+    assert len(t2) == 4 and all(depth[n] == 2 for n in t2)
+    # unbounded depth -> every leaf is a task
+    tl = sharding.initial_tasks(csr, 2 ** 31 - 1)
+    assert len(tl) == 16 and all(csr.nChildren(n) == 0 for n in tl)
+    # ragged tree: a leaf above the cut is its own task
+    ds = d.MultiLevelDataset(rows=[["R", "a", "x", "3", "1"], ["R", "b", "4", "2"]])
+    c2 = ds.getTree().to_csr()
+    names = sorted(c2.nodes[n].toString() for n in sharding.initial_tasks(c2, 2))
+    assert names == ["R-a-x", "R-b"]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_plan_covers_tree_once(world):
+    ds = d.MultiLevelDataset(rows=synth.nys_shaped_rows())
+    csr = ds.getTree().to_csr()
+    plan = sharding.make_plan(csr, 2, world)
+    assert len(plan.tasks) == 32
+    sizes = csr.subtree_sizes()
+    covered = sum(int(sizes[t]) for t in plan.tasks) + sum(len(l.nodes) for l in plan.top_levels)
+    assert covered == csr.nNodes
+    loads = [sum(int(sizes[t]) for t in plan.my_tasks(r)) for r in range(world)]
+    assert max(loads) <= 1.35 * (sum(loads) / world) + max(int(sizes[t]) for t in plan.tasks) * (world > 4)
+    for lvl in plan.top_levels:
+        for child, src, dst in lvl.transfers:
+            assert src != dst and plan.node_owner[child] == src
+    # the default (unbounded) depth is coarsened automatically
+    auto = sharding.make_plan(csr, 2 ** 31 - 1, world)
+    assert len(auto.tasks) >= min(4 * world, 700) or world == 1
+
+
+# ---- multi-rank plumbing over gloo with a CPU stand-in for the engine --------------------------------
+
+class FakeEngine:
+    """Deterministic CPU stand-in: a node's 'population' is 4 doubles computed from its id and its
+    children's populations in child order, so any mistake in the schedule, the owners or the
+    pack/send/recv/unpack path changes the root value."""
+
+    def __init__(self, ddc):
+        self.csr = ddc.csr
+        self.pop = {}
+        self.nNodes = self.csr.nNodes
+
+        class O:
+            device = 0
+
+        self.options = O()
+        self.N = 4
+        self._launch = 0
+
+    def _kids(self, n):
+        return [int(c) for c in self.csr.children[self.csr.childOffsets[n]:self.csr.childOffsets[n + 1]]]
+
+    def _compute(self, n):
+        v = np.array([n + 1.0, 0.5 * n, 1.0, -n], dtype=np.float64)
+        for k, c in enumerate(self._kids(n)):
+            v = v * 0.75 + (k + 1) * np.roll(self.pop[c], k + 1) + 0.001 * self.pop[c][0] * v[2]
+        self.pop[n] = v
+        for c in self._kids(n):
+            del self.pop[c]
+
+    def _rec(self, n):
+        if n in self.pop:
+            return
+        for c in self._kids(n):
+            self._rec(c)
+        self._compute(n)
+
+    def reset_populations(self):
+        self.pop = {}
+        self.done = set()
+
+    def run_subtrees(self, roots):
+        for r in roots:
+            self._rec(r)
+        self.done.update(roots)
+
+    def run_nodes(self, nodes):
+        for n in nodes:
+            self._compute(n)
+
+    def run(self):
+        self.reset_populations()
+        self._rec(0)
+
+    def packed_bytes(self):
+        return 32
+
+    def pack(self, node, ptr):
+        C.memmove(ptr, self.pop[node].ctypes.data, 32)
+
+    def unpack(self, node, ptr):
+        a = np.empty(4)
+        C.memmove(a.ctypes.data, ptr, 32)
+        self.pop[node] = a
+
+    def release(self, node):
+        self.pop.pop(node, None)
+
+    def all_node_stats(self):
+        z = np.zeros(self.nNodes)
+        ls = z.copy()
+        for n, v in self.pop.items():
+            ls[n] = v.sum()
+        return dict(ess=z + 1, relEss=z + 1, logNormEstimate=ls, logScaling=ls, resampled=np.zeros(self.nNodes, np.int32),
+                    done=np.ones(self.nNodes, np.int32))
+
+    def run_info(self):
+        class I:
+            deviceMs = 0.0
+            kernelLaunches = 0
+            particleUpdates = 0
+            algorithmicBytes = 0
+            h2dBytes = 0
+            d2hBytes = 0
+
+        return I()
+
+
+def _gloo_worker(rank, world, port, depth_opt, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows(seed=3, nGroups=5))
+        ddc = d.DistributedDC.createInstance(d.DCOptions(nParticles=4, maximumDistributionDepth=depth_opt),
+                                             d.MultiLevelProposalFactory(dataset=ds), ds.getTree())
+        ddc.engineFactory = FakeEngine
+        ddc.run()
+        q.put((rank, float(ddc.stats["logScaling"][0]), ddc.rootOwner, ddc.lastRun["nvlinkBytes"]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("depth_opt", [1, 2, 2 ** 31 - 1])
+def test_two_rank_sharded_run_equals_single_process(depth_opt):
+    import torch.multiprocessing as mp
+
+    ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows(seed=3, nGroups=5))
+    single = d.DistributedDC.createInstance(d.DCOptions(nParticles=4), d.MultiLevelProposalFactory(dataset=ds), ds.getTree())
+    single.engineFactory = FakeEngine
+    single.run()
+    expect = float(single.stats["logScaling"][0])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (depth_opt % 7)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, depth_opt, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, val, owner, moved in res:
+        assert val == expect, (rank, val, expect)
+    assert sum(r[3] for r in res) > 0  # something actually crossed ranks
