@@ -137,111 +137,164 @@ def algorithmic_bytes(csr, N, multinomial):
     return per, total
 
 
+def make_ddc(args, wl, local):
+    import dcsmc_b200 as d
+
+    scheme = d.ResamplingScheme.MULTINOMIAL if args.scheme == "multinomial" else d.ResamplingScheme.STRATIFIED
+    opt = d.DCOptions(nParticles=args.particles, masterRandomSeed=31, resamplingScheme=scheme,
+                      maximumDistributionDepth=args.depth_cut)
+    if wl["rows"] is not None:
+        ds = d.MultiLevelDataset(rows=wl["rows"])
+        factory = d.MultiLevelProposalFactory(dataset=ds)
+        tree = ds.getTree()
+    else:
+        tree = d.perfectBinaryTree(args.depth)
+        csr = tree.to_csr()
+        factory = d.GaussianLeafProposalFactory({n: float(wl["leafObs"][i]) for i, n in enumerate(csr.nodes)})
+    return d.DistributedDC.createInstance(opt, factory, tree, device=local), factory
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from dcsmc_b200 import _ffi
-    from dcsmc_b200.engine import Engine
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
     wl = build_workload(args)
     csr = wl["csr"]
     N = args.particles
     multinomial = args.scheme == "multinomial"
-    scheme = _ffi.MULTINOMIAL if multinomial else _ffi.STRATIFIED
+    ddc, factory = make_ddc(args, wl, local)
 
-    if world > 1:
-        raise SystemExit("multi-GPU bench not wired yet")
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
 
-    e = Engine(nParticles=N, masterRandomSeed=31, resamplingScheme=scheme, device=local)
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def upload():
-        e.set_tree(csr)
-        e.set_multilevel_model(wl["nT"], wl["nS"], wl["leafKind"], wl["leafObs"])
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
 
     sampler = ClockSampler(local)
     sampler.start()
-    upload()
     for _ in range(args.warmup):
-        e.run()
-    torch.cuda.synchronize()
+        ddc.run()
+    barrier()
 
-    # ---- timed region 1: device-resident inputs, CUDA events on the engine's stream -------------
+    # ---- timed region 1: device-resident inputs ------------------------------------------------------
+    # 1 GPU: CUDA events recorded by the engine on its own launching stream around the whole run.
+    # N GPUs: CUDA events on the current stream bracketing K runs (each run ends with a stream sync),
+    # max over ranks.
     sampler.window_begin()
-    dev_ms, launches = 0.0, 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_ms = 0.0
+    launches = updates = alg_bytes = nvlink = 0
+    barrier()
+    ev0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e.run()
-        info = e.run_info()
-        dev_ms += info.deviceMs
-        launches += info.kernelLaunches
-    torch.cuda.synchronize()
+        ddc.run()
+        lr = ddc.lastRun
+        dev_ms += lr["deviceMs"]
+        launches += lr["kernelLaunches"]
+        updates += lr["particleUpdates"]
+        alg_bytes += lr["algorithmicBytes"]
+        nvlink += lr["nvlinkBytes"]
+    ev1.record()
+    barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.window_end()
-    updates_per_step = info.particleUpdates
-    alg_bytes_step = info.algorithmicBytes
-    ms_per_step = dev_ms / args.steps
+    if world == 1:
+        total_ms = dev_ms
+    else:
+        total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    updates_per_step = sum_over_ranks(updates) / args.steps
+    alg_bytes_step = sum_over_ranks(alg_bytes) / args.steps
+    launches = int(sum_over_ranks(launches))
+    nvlink = sum_over_ranks(nvlink) / args.steps
+    ms_per_step = total_ms / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
 
-    # ---- timed region 2: end to end through the C ABI with HOST buffers ---------------------------
-    # every step re-uploads the topology + model from host arrays and reads the per-node statistics
-    # and the root population back to the host.
+    # ---- timed region 2: end to end through the public API with HOST buffers ---------------------------
+    # every step re-uploads the topology + model from host arrays (set_tree / set_*_model) and reads
+    # the per-node statistics and the root population back to the host.
     h2d = d2h = 0
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        upload()
-        e.run()
-        info2 = e.run_info()
-        st = e.all_node_stats()
-        rs, _, rw = e.population(0)
-        h2d = info2.h2dBytes
-        d2h = info2.d2hBytes + rs.nbytes + rw.nbytes
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        ddc.engine.set_tree(ddc.csr)
+        factory.configure(ddc.engine, ddc.csr)
+        ddc.run()
+        st = ddc.stats
+        h2d = ddc.lastRun["h2dBytes"]
+        d2h = ddc.lastRun["d2hBytes"]
+        if rank == ddc.rootOwner:
+            rs, _, rw = ddc.engine.population(0)
+            d2h += rs.nbytes + rw.nbytes
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     e2e_value = updates_per_step / (e2e_ms * 1e-3)
     sampler.window_end()  # the clock window covers both timed regions
     clocks = sampler.stop()
     logZ = float(st["logNormEstimate"][0])
 
     # ---- per-kernel-class timing (one extra profiled step, outside the timed regions) -------------
-    e.profile_enable(True)
-    e.run()
-    prof = e.profile()
-    e.profile_enable(False)
-    per_bytes, total_bytes = algorithmic_bytes(csr, N, multinomial)
-    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
-    peak, peak_src = load_peaks()
-    dom_ms = prof[dom]["ms"]
-    dom_launches = max(1, prof[dom]["launches"])
-    dom_bytes = per_bytes.get(dom, 0)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(dom)
-        except Exception:
-            traffic = None
-    roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-        "launch_ms": round(dom_ms / dom_launches, 4), "bytes_per_launch": int(dom_bytes / dom_launches),
-        "kernel_share_of_step": round(dom_ms / tot_ms, 4),
-        "step": {"achieved": round(alg_bytes_step / (ms_per_step * 1e-3) / 1e9, 1),
-                 "frac": round(alg_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak, 4),
-                 "bytes_per_update": round(alg_bytes_step / updates_per_step, 1)},
-        "by_kernel_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]},
-    }
+    roofline = None
+    if rank == 0:
+        e = ddc.engine
+        e.profile_enable(True)
+        if world == 1:
+            e.run()
+        else:
+            e.reset_populations()
+            e.run_subtrees(ddc.plan.my_tasks(rank))
+        prof = e.profile()
+        e.profile_enable(False)
+        frac_of_tree = 1.0 if world == 1 else e.run_info().particleUpdates / float(csr.nNodes * N)
+        per_bytes, total_bytes = algorithmic_bytes(csr, N, multinomial)
+        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
+        peak, peak_src = load_peaks()
+        dom_ms = prof[dom]["ms"]
+        dom_launches = max(1, prof[dom]["launches"])
+        dom_bytes = per_bytes.get(dom, 0) * frac_of_tree
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dom)
+            except Exception:
+                traffic = None
+        step_gbs = alg_bytes_step / (ms_per_step * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            "launch_ms": round(dom_ms / dom_launches, 4), "bytes_per_launch": int(dom_bytes / dom_launches),
+            "kernel_share_of_step": round(dom_ms / tot_ms, 4),
+            "step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / (peak * world), 4),
+                     "frac_of_nominal_8TBs": round(step_gbs / (8000.0 * world), 4),
+                     "bytes_per_update": round(alg_bytes_step / updates_per_step, 1)},
+            "by_kernel_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]},
+        }
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args, wl)
 
     line = {
@@ -250,11 +303,13 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "nParticles": N, "resamplingScheme": args.scheme,
                    "relativeEssThreshold": "1+1e-10 (resample every node)", "rng": "philox4x32-10",
+                   "maximumDistributionDepth": args.depth_cut,
                    "l2_policy": "inputs larger than L2 (>=10 GB of particle state per step)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
+        "nvlink_bytes_per_step": int(nvlink),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "wall_ms_per_step": wall_ms / args.steps,
@@ -262,8 +317,9 @@ def run_ours(args):
     }
     if rank == 0:
         print(json.dumps(line))
-    e.close()
+    ddc.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -358,8 +414,10 @@ def main():
     ap.add_argument("--workload", default="nys", choices=["nys", "binary16"])
     ap.add_argument("--depth", type=int, default=16)
     ap.add_argument("--particles", type=int, default=100_000)
-    ap.add_argument("--scheme", default="stratified", choices=["multinomial", "stratified"])
+    ap.add_argument("--scheme", default="multinomial", choices=["multinomial", "stratified"],
+                    help="DCOptions.resamplingScheme (reference default: MULTINOMIAL)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth-cut", type=int, default=2, help="DCOptions.maximumDistributionDepth (subtree sharding cut)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

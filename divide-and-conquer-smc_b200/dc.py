@@ -347,11 +347,26 @@ class DistributedDC:
         rank, world = dist.get_rank(), dist.get_world_size()
         self.nWorkers = world
         e = self.engine
-        plan = sharding.make_plan(self.csr, self.options.maximumDistributionDepth, world)
-        self.plan = plan
-        e.reset_populations()
         dev = torch.device("cuda", e.options.device) if torch.cuda.is_available() else torch.device("cpu")
         nbytes = e.packed_bytes()
+        if getattr(self, "plan", None) is None or self._planWorld != world:
+            # the schedule is static: plan, node->owner map and transfer buffers are built once
+            plan = sharding.make_plan(self.csr, self.options.maximumDistributionDepth, world)
+            own = np.array([plan.node_owner.get(n, -1) for n in range(self.csr.nNodes)])
+            for t in plan.tasks:  # nodes strictly inside a task subtree belong to the task's owner
+                stack = [t]
+                while stack:
+                    n = stack.pop()
+                    own[n] = plan.task_owner[t]
+                    stack.extend(int(c) for c in self.csr.children[self.csr.childOffsets[n]:self.csr.childOffsets[n + 1]])
+            self.plan, self._planWorld, self._nodeOwner = plan, world, own
+            self._xferBufs = {}
+            for lvl in plan.top_levels:
+                for child, src, dst in lvl.transfers:
+                    if rank in (src, dst):
+                        self._xferBufs[child] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        plan, own = self.plan, self._nodeOwner
+        e.reset_populations()
         launches = updates = algbytes = nvbytes = 0
         devms = 0.0
 
@@ -371,13 +386,13 @@ class DistributedDC:
             ops, recvs, sends = [], [], []
             for child, src, dst in lvl.transfers:
                 if rank == src:
-                    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    buf = self._xferBufs[child]
                     e.pack(child, buf.data_ptr())
                     launches += 1
                     sends.append((child, buf))
                     ops.append(dist.P2POp(dist.isend, buf, dst))
                 elif rank == dst:
-                    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    buf = self._xferBufs[child]
                     recvs.append((child, buf))
                     ops.append(dist.P2POp(dist.irecv, buf, src))
             if ops:
@@ -397,14 +412,6 @@ class DistributedDC:
                 account()
         # every rank learns every node's statistics (each node was computed on exactly one rank)
         st = e.all_node_stats()
-        own = np.array([plan.node_owner.get(n, -1) for n in range(self.csr.nNodes)])
-        # nodes strictly inside a task subtree belong to the task's owner
-        for t in plan.tasks:
-            stack = [t]
-            while stack:
-                n = stack.pop()
-                own[n] = plan.task_owner[t]
-                stack.extend(int(c) for c in self.csr.children[self.csr.childOffsets[n]:self.csr.childOffsets[n + 1]])
         keys = ["ess", "relEss", "logNormEstimate", "logScaling"]
         mat = np.stack([np.where(own == rank, st[k], 0.0) for k in keys] + [np.where(own == rank, st["resampled"], 0).astype(np.float64)])
         tens = torch.from_numpy(mat).to(dev)
