@@ -490,6 +490,9 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   const int tilesR = (N + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
   const long long gridP = (long long)st.count * tilesP;
   if (gridP > 0x7fffffffLL) return e->fail(DCSMC_EINVAL, "step too large for one launch");
+  // multilevel leaves: rESS == 1 exactly, so the resample decision is known on the host and the
+  // leaf kernel does the dart work itself (k_finalize still records the statistics)
+  const bool leafFused = st.leaf && e->model == DCSMC_MODEL_MULTILEVEL && 1.0 < e->opt.relativeEssThreshold;
 
   if (e->model == DCSMC_MODEL_MARKOV) {
     ProfScope p(e, DCSMC_K_MARKOV);
@@ -499,9 +502,14 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
     int CH = (N + LEAF_WARPS - 1) / LEAF_WARPS;
     CH = std::min(512, std::max(32, (CH + 31) / 32 * 32));
     const int blocksPerNode = (N + LEAF_WARPS * CH - 1) / (LEAF_WARPS * CH);
+    if (leafFused && e->opt.resamplingScheme == DCSMC_MULTINOMIAL) {
+      c.offspring = e->dOffspring;
+      CK(cudaMemsetAsync(e->dOffspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), e->stream));
+    }
+    const int mode = !leafFused ? 0 : (e->opt.resamplingScheme == DCSMC_STRATIFIED ? 1 : 2);
     ProfScope p(e, DCSMC_K_LEAF);
     k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS,
-                          LEAF_WARPS * CH * sizeof(double), e->stream>>>(c, blocksPerNode, CH);
+                          LEAF_WARPS * CH * sizeof(double), e->stream>>>(c, blocksPerNode, CH, mode);
   } else {
     ProfScope p(e, DCSMC_K_INTERNAL);
     k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
@@ -524,8 +532,10 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
     k_finalize<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
   }
   if (e->opt.resamplingScheme == DCSMC_STRATIFIED) {
-    ProfScope p(e, DCSMC_K_RESAMPLE);
-    k_resample_stratified<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+    if (!leafFused) {
+      ProfScope p(e, DCSMC_K_RESAMPLE);
+      k_resample_stratified<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+    }
   } else {
     // multinomial: offspring counts by atomics, then scan + expansion (no dart sort)
     const int tilesE = (N + EXPAND_TILE - 1) / EXPAND_TILE;
@@ -533,8 +543,8 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
     c.offspring = e->dOffspring;
     c.descA = e->dDesc;
     c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + needDescE);
-    CK(cudaMemsetAsync(e->dOffspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), e->stream));
-    {
+    if (!leafFused) {
+      CK(cudaMemsetAsync(e->dOffspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), e->stream));
       ProfScope p(e, DCSMC_K_DARTS);
       k_darts_count<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
     }
