@@ -89,6 +89,10 @@ struct dcsmc_engine {
   size_t cdfCap = 0;
   unsigned long long* dDesc = nullptr;  // descA | descB | ticket
   size_t descCap = 0;
+  int32_t* dInvTable = nullptr;  // inverse-CDF index of the internal nodes of a step
+  size_t invTableCap = 0;
+  int invB = 1;
+  size_t leafSmemSet[3] = {0, 0, 0};
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
   size_t offspringCap = 0;
 
@@ -507,9 +511,14 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
       CK(cudaMemsetAsync(e->dOffspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), e->stream));
     }
     const int mode = !leafFused ? 0 : (e->opt.resamplingScheme == DCSMC_STRATIFIED ? 1 : 2);
+    const size_t leafSmem = LEAF_WARPS * leaf_warp_smem_bytes(CH);
+    if (leafSmem > e->leafSmemSet[RNG]) {  // > 48 KB of dynamic shared memory needs the opt-in
+      CK(cudaFuncSetAttribute(k_leaf_propose<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leafSmem));
+      e->leafSmemSet[RNG] = leafSmem;
+    }
     ProfScope p(e, DCSMC_K_LEAF);
     k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS,
-                          LEAF_WARPS * CH * sizeof(double), e->stream>>>(c, blocksPerNode, CH, mode);
+                          leafSmem, e->stream>>>(c, blocksPerNode, CH, mode);
   } else {
     ProfScope p(e, DCSMC_K_INTERNAL);
     k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
@@ -530,6 +539,11 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   {
     ProfScope p(e, DCSMC_K_FINALIZE);
     k_finalize<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
+  }
+  if (!st.leaf) {
+    const int tilesT = (c.invB + 1 + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
+    ProfScope p(e, DCSMC_K_RESAMPLE);
+    k_build_inverse_table<<<(unsigned)(st.count * tilesT), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesT);
   }
   if (e->opt.resamplingScheme == DCSMC_STRATIFIED) {
     if (!leafFused) {
@@ -584,6 +598,8 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.dN = (double)N;
   c.threshold = e->opt.relativeEssThreshold;
   c.cdf = e->dCdf;
+  c.invTable = e->dInvTable;
+  c.invB = e->invB;
   c.uniformLogW = uniformLeafLogW(e);
   return DCSMC_OK;
 }
@@ -631,6 +647,9 @@ int executePlan(dcsmc_engine* e, Plan& plan) {
     if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL) needDesc = std::max(needDesc, maxStep * tilesE + 1);
     CK(grow((void**)&e->dDesc, e->descCap, needDesc, sizeof(unsigned long long)));
   }
+  e->invB = 1;
+  while ((size_t)e->invB * 8 < (size_t)N) e->invB <<= 1;
+  CK(grow((void**)&e->dInvTable, e->invTableCap, std::max<size_t>(1, maxInternalStep * ((size_t)e->invB + 1)), sizeof(int32_t)));
   if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL)
     CK(grow((void**)&e->dOffspring, e->offspringCap, maxStep * (size_t)e->Npad, sizeof(int32_t)));
   if (plan.stepNodes.size() > e->stepNodesCap) {
@@ -801,7 +820,7 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   for (double* p : e->injDev)
     if (p) cudaFree(p);
   void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dInj, e->dJavaState,
-                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring};
+                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (e->ev0) cudaEventDestroy(e->ev0);
