@@ -39,6 +39,23 @@ struct Slot {
   size_t bytes = 0;
 };
 
+struct Plan {
+  std::vector<Step> steps;
+  std::vector<int32_t> stepNodes;
+};
+
+// A plan made on an empty pool is a pure function of (tree, model, options, roots): cached together
+// with the pool state it leaves behind, so repeated runs skip planning and descriptor uploads.
+struct CachedPlan {
+  std::vector<int> roots;
+  Plan plan;
+  std::multimap<size_t, size_t> freeBySize;
+  size_t poolTop = 0;
+  std::vector<Slot> slot;
+  std::vector<char> resident, imported;
+  bool uploaded = false;  // this plan's step lists / node descriptors are the ones on the device
+};
+
 }  // namespace
 
 struct dcsmc_engine {
@@ -93,6 +110,8 @@ struct dcsmc_engine {
   size_t invTableCap = 0;
   int invB = 1;
   size_t leafSmemSet[3] = {0, 0, 0};
+  std::vector<CachedPlan> planCache;
+  const CachedPlan* devicePlan = nullptr;  // whose descriptors are currently uploaded
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
   size_t offspringCap = 0;
 
@@ -290,6 +309,8 @@ int uploadTables(dcsmc_engine* e) {
   e->hNodes.assign(nN, NodeDev{});
   e->hStats.assign(nN, dcsmc_node_stats_t{});
   e->slot.assign(nN, Slot{});
+  e->planCache.clear();
+  e->devicePlan = nullptr;
   e->resident.assign(nN, 0);
   e->imported.assign(nN, 0);
   e->freeBySize.clear();
@@ -337,11 +358,6 @@ int ensurePool(dcsmc_engine* e) {
 }
 
 // ---- planning --------------------------------------------------------------------------------
-
-struct Plan {
-  std::vector<Step> steps;
-  std::vector<int32_t> stepNodes;
-};
 
 void collectSubtree(const dcsmc_engine* e, int r, std::vector<int>& out) {
   std::vector<int> stack{r};
@@ -622,7 +638,7 @@ int validateForRun(dcsmc_engine* e) {
 }
 
 // run a plan: upload step lists, execute, fetch stats
-int executePlan(dcsmc_engine* e, Plan& plan) {
+int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr) {
   int rc;
   const int N = e->opt.nParticles;
   // scratch sizing: CDF + look-back descriptors for internal steps, darts for multinomial
@@ -652,17 +668,21 @@ int executePlan(dcsmc_engine* e, Plan& plan) {
   CK(grow((void**)&e->dInvTable, e->invTableCap, std::max<size_t>(1, maxInternalStep * ((size_t)e->invB + 1)), sizeof(int32_t)));
   if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL)
     CK(grow((void**)&e->dOffspring, e->offspringCap, maxStep * (size_t)e->Npad, sizeof(int32_t)));
-  if (plan.stepNodes.size() > e->stepNodesCap) {
-    if (e->dStepNodes) cudaFree(e->dStepNodes);
-    e->dStepNodes = nullptr;
-    CK(cudaMalloc((void**)&e->dStepNodes, plan.stepNodes.size() * sizeof(int32_t)));
-    e->stepNodesCap = plan.stepNodes.size();
+  const bool descriptorsOnDevice = cached != nullptr && e->devicePlan == cached;
+  if (!descriptorsOnDevice) {
+    if (plan.stepNodes.size() > e->stepNodesCap) {
+      if (e->dStepNodes) cudaFree(e->dStepNodes);
+      e->dStepNodes = nullptr;
+      CK(cudaMalloc((void**)&e->dStepNodes, plan.stepNodes.size() * sizeof(int32_t)));
+      e->stepNodesCap = plan.stepNodes.size();
+    }
+    CK(cudaMemcpyAsync(e->dStepNodes, plan.stepNodes.data(), plan.stepNodes.size() * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, e->stream));
+    // node descriptors for every node touched by the plan
+    for (int n : plan.stepNodes) fillNodeDev(e, n);
+    CK(cudaMemcpyAsync(e->dNodes, e->hNodes.data(), sizeof(NodeDev) * e->nNodes, cudaMemcpyHostToDevice, e->stream));
+    e->devicePlan = cached;
   }
-  CK(cudaMemcpyAsync(e->dStepNodes, plan.stepNodes.data(), plan.stepNodes.size() * sizeof(int32_t),
-                     cudaMemcpyHostToDevice, e->stream));
-  // node descriptors for every node touched by the plan
-  for (int n : plan.stepNodes) fillNodeDev(e, n);
-  CK(cudaMemcpyAsync(e->dNodes, e->hNodes.data(), sizeof(NodeDev) * e->nNodes, cudaMemcpyHostToDevice, e->stream));
   // accumulators of the nodes about to be recomputed start from zero
   if (!plan.stepNodes.empty()) {
     const int n = (int)plan.stepNodes.size();
@@ -673,7 +693,7 @@ int executePlan(dcsmc_engine* e, Plan& plan) {
   makeCtx(e, c);
   e->info = dcsmc_run_info{};
   e->info.poolBytes = (int64_t)e->poolBytes;
-  e->info.h2dBytes = e->pendingH2D + (int64_t)(plan.stepNodes.size() * sizeof(int32_t) + sizeof(NodeDev) * e->nNodes);
+  e->info.h2dBytes = e->pendingH2D + (descriptorsOnDevice ? 0 : (int64_t)(plan.stepNodes.size() * sizeof(int32_t) + sizeof(NodeDev) * e->nNodes));
   e->info.d2hBytes = (int64_t)(sizeof(NodeStats) * e->nNodes);
   e->pendingH2D = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
@@ -739,8 +759,40 @@ int prepare(dcsmc_engine* e) {
 int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
   int rc;
   if ((rc = prepare(e))) return rc;
+  bool emptyPool = e->poolTop == 0;
+  if (emptyPool)
+    for (char r : e->resident)
+      if (r) {
+        emptyPool = false;
+        break;
+      }
+  if (emptyPool) {
+    for (CachedPlan& cp : e->planCache)
+      if (cp.roots == roots) {
+        e->freeBySize = cp.freeBySize;
+        e->poolTop = cp.poolTop;
+        e->slot = cp.slot;
+        e->resident = cp.resident;
+        e->imported = cp.imported;
+        return executePlan(e, cp.plan, &cp);
+      }
+  }
   Plan plan;
   if ((rc = planRoots(e, roots, plan))) return rc;
+  if (emptyPool && e->planCache.size() < 4) {
+    e->planCache.reserve(4);  // keeps &planCache[k] stable (devicePlan points into it)
+    CachedPlan cp;
+    cp.roots = roots;
+    cp.plan = plan;
+    cp.freeBySize = e->freeBySize;
+    cp.poolTop = e->poolTop;
+    cp.slot = e->slot;
+    cp.resident = e->resident;
+    cp.imported = e->imported;
+    e->planCache.push_back(std::move(cp));
+    return executePlan(e, e->planCache.back().plan, &e->planCache.back());
+  }
+  e->devicePlan = nullptr;
   return executePlan(e, plan);
 }
 
@@ -1121,6 +1173,7 @@ int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* devic
     return e->fail(DCSMC_ENOMEM, "population pool (%zu bytes) cannot hold the unpacked node %d", e->poolBytes, node);
   }
   fillNodeDev(e, node);
+  e->devicePlan = nullptr;
   CK(cudaMemcpyAsync(e->dNodes + node, &e->hNodes[node], sizeof(NodeDev), cudaMemcpyHostToDevice, e->stream));
   RunCtx c;
   makeCtx(e, c);
