@@ -49,7 +49,7 @@ struct Plan {
 struct CachedPlan {
   std::vector<int> roots;
   Plan plan;
-  std::multimap<size_t, size_t> freeBySize;
+  std::map<size_t, size_t> freeBySize;
   size_t poolTop = 0;
   std::vector<Slot> slot;
   std::vector<char> resident, imported;
@@ -92,7 +92,7 @@ struct dcsmc_engine {
   char* pool = nullptr;
   size_t poolBytes = 0;
   bool poolIsBudget = false;  // pool was capped by the memory budget
-  std::multimap<size_t, size_t> freeBySize;  // bytes -> offset (exact-size free lists)
+  std::map<size_t, size_t> freeBySize;  // free holes below poolTop: offset -> bytes (coalesced)
   size_t poolTop = 0;
   std::vector<Slot> slot;        // per node
   std::vector<char> resident;    // per node
@@ -177,18 +177,32 @@ size_t slotBytes(const dcsmc_engine* e, int n) {
 
 void poolFree(dcsmc_engine* e, int n);
 
+// Population pool: a bump pointer (poolTop) plus coalesced free holes below it. Best fit over the
+// holes first, then the hole touching poolTop is extended, then fresh space. All of this runs at
+// plan time on the host; the device only ever sees final addresses.
 bool poolAlloc(dcsmc_engine* e, int n) {
   poolFree(e, n);  // recomputing a node reuses nothing of its old population
   const size_t b = slotBytes(e, n);
-  auto it = e->freeBySize.find(b);
+  auto best = e->freeBySize.end();
+  for (auto it = e->freeBySize.begin(); it != e->freeBySize.end(); ++it)
+    if (it->second >= b && (best == e->freeBySize.end() || it->second < best->second)) best = it;
   size_t off;
-  if (it != e->freeBySize.end()) {
-    off = it->second;
-    e->freeBySize.erase(it);
+  if (best != e->freeBySize.end()) {
+    off = best->first;
+    const size_t rest = best->second - b;
+    e->freeBySize.erase(best);
+    if (rest) e->freeBySize.emplace(off + b, rest);
   } else {
-    if (e->poolTop + b > e->poolBytes) return false;
-    off = e->poolTop;
-    e->poolTop += b;
+    // extend the hole that ends at poolTop, if any
+    size_t start = e->poolTop;
+    if (!e->freeBySize.empty()) {
+      auto last = std::prev(e->freeBySize.end());
+      if (last->first + last->second == e->poolTop) start = last->first;
+    }
+    if (start + b > e->poolBytes) return false;
+    if (start != e->poolTop) e->freeBySize.erase(std::prev(e->freeBySize.end()));
+    off = start;
+    e->poolTop = start + b;
   }
   e->slot[n] = Slot{off, b};
   e->resident[n] = 1;
@@ -197,8 +211,25 @@ bool poolAlloc(dcsmc_engine* e, int n) {
 
 void poolFree(dcsmc_engine* e, int n) {
   if (!e->resident[n]) return;
-  e->freeBySize.emplace(e->slot[n].bytes, e->slot[n].offset);
   e->resident[n] = 0;
+  size_t off = e->slot[n].offset, len = e->slot[n].bytes;
+  auto next = e->freeBySize.lower_bound(off);
+  if (next != e->freeBySize.begin()) {
+    auto prev = std::prev(next);
+    if (prev->first + prev->second == off) {
+      off = prev->first;
+      len += prev->second;
+      e->freeBySize.erase(prev);
+    }
+  }
+  if (next != e->freeBySize.end() && off + len == next->first) {
+    len += next->second;
+    e->freeBySize.erase(next);
+  }
+  if (off + len == e->poolTop)
+    e->poolTop = off;  // the hole touches the top: give it back
+  else
+    e->freeBySize.emplace(off, len);
 }
 
 void fillNodeDev(dcsmc_engine* e, int n) {
@@ -405,7 +436,7 @@ bool emitLevels(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan, bool
 }
 
 struct PoolState {
-  std::multimap<size_t, size_t> freeBySize;
+  std::map<size_t, size_t> freeBySize;
   size_t poolTop;
   std::vector<Slot> slot;
   std::vector<char> resident, imported;
