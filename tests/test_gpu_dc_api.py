@@ -142,3 +142,28 @@ def test_sharded_run_is_bit_identical_to_single_gpu(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI_GPU_CHECK_OK" in r.stdout
+
+
+def test_native_cli_run_matches_engine(tmp_path):
+    """scripts/run-distributed.sh equivalent: dcsmc_ddc with the reference's flags writes the
+    DefaultProcessorFactory outputs; logZ equals the Python-driven run and the oracle."""
+    rows = synth.small_multilevel_rows(seed=4)
+    path = tmp_path / "data.csv"
+    synth.write_csv(rows, str(path))
+    cli = os.path.join(ROOT, "divide-and-conquer-smc_b200", "csrc", "dcsmc_ddc")
+    res = tmp_path / "results" / "latest"
+    r = subprocess.run([cli, "-dataFile", str(path), "-nParticles", "5000", "-resamplingScheme", "STRATIFIED",
+                        "-dc.masterRandomSeed", "31", "-nThreadsPerNode", "4", "-maximumDistributionDepth", "2",
+                        "-resultsFolder", str(res)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ds = d.MultiLevelDataset(str(path))
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    ref = o.run(csr, 5000, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
+    assert float(open(res / "logZ").read()) == ref.logNormEstimate[0]
+    lines = open(res / "timing.csv").read().strip().splitlines()
+    assert len(lines) == csr.nNodes + 1
+    last = lines[-1].split(",")
+    assert last[0] == csr.nodes[0].toString() and float(last[1]) == ref.ess[0] and float(last[3]) == ref.logNormEstimate[0]
+    assert "timing: node=" in r.stdout and "logZ estimate" in r.stdout

@@ -257,3 +257,30 @@ def test_two_rank_sharded_run_equals_single_process(depth_opt):
     for rank, val, owner, moved in res:
         assert val == expect, (rank, val, expect)
     assert sum(r[3] for r in res) > 0  # something actually crossed ranks
+
+
+def test_native_cli_dataset_loader_matches_python_mirror(tmp_path):
+    """dcsmc_ddc (C++ mirror of DDCMain + MultiLevelDataset + Node.hashCode) builds the same CSR,
+    child order, hash codes and leaf data as the Python mirror — on the NYS-shaped file too."""
+    import subprocess
+
+    cli = os.path.join(ROOT, "divide-and-conquer-smc_b200", "csrc", "dcsmc_ddc")
+    assert os.path.exists(cli), "build with __graft_entry__.build()"
+    for rows in (synth.small_multilevel_rows(seed=3), synth.nys_shaped_rows()[:600]):
+        p = tmp_path / "d.csv"
+        synth.write_csv(rows, str(p))
+        out = subprocess.run([cli, "-dataFile", str(p), "-dumpTree"], capture_output=True, text=True, check=True).stdout
+        ds = d.MultiLevelDataset(str(p))
+        csr = ds.getTree().to_csr()
+        nT, nS = ds.leaf_arrays(csr)
+        lines = out.strip().splitlines()
+        assert lines[0] == f"nNodes {csr.nNodes}"
+        for i, l in enumerate(lines[1:]):
+            f = l.split()
+            assert f[1] == csr.nodes[i].toString()
+            assert int(f[3]) == csr.javaHash[i] and int(f[5]) == nT[i] and int(f[7]) == nS[i]
+            assert [int(x) for x in f[9:]] == list(csr.children[csr.childOffsets[i]:csr.childOffsets[i + 1]])
+    r = subprocess.run([cli, "-nParticles", "10"], capture_output=True, text=True)
+    assert r.returncode == 2 and "dataFile is required" in r.stderr
+    r = subprocess.run([cli, "-dataFile", str(p), "-resamplingScheme", "SYSTEMATIC"], capture_output=True, text=True)
+    assert r.returncode == 2
