@@ -543,7 +543,8 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   if (gridP > 0x7fffffffLL) return e->fail(DCSMC_EINVAL, "step too large for one launch");
   // multilevel leaves: rESS == 1 exactly, so the resample decision is known on the host and the
   // leaf kernel does the dart work itself (k_finalize still records the statistics)
-  const bool leafFused = st.leaf && e->model == DCSMC_MODEL_MULTILEVEL && 1.0 < e->opt.relativeEssThreshold;
+  const bool javaSums = e->opt.sumMode == DCSMC_SUM_JAVA;
+  const bool leafFused = !javaSums && st.leaf && e->model == DCSMC_MODEL_MULTILEVEL && 1.0 < e->opt.relativeEssThreshold;
 
   if (e->model == DCSMC_MODEL_MARKOV) {
     ProfScope p(e, DCSMC_K_MARKOV);
@@ -574,20 +575,25 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
     // all weights equal: the exact sums are known in closed form, no scan and no CDF
     ProfScope p(e, DCSMC_K_FINALIZE);
     k_uniform_stats<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
-  } else {
-    const size_t needDesc = (size_t)st.count * tilesS;
-    c.descA = e->dDesc;
-    c.descB = e->dDesc + needDesc;
-    c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + 2 * needDesc);
-    CK(cudaMemsetAsync(e->dDesc, 0, (2 * needDesc + 1) * sizeof(unsigned long long), e->stream));
-    ProfScope p(e, DCSMC_K_SCAN);
-    k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, e->stream>>>(c, tilesS);
   }
-  {
+  if (javaSums) {
+    // parity mode: the reference's sequential sums (also finalises the node statistics)
+    ProfScope p(e, DCSMC_K_SCAN);
+    k_scan_java<<<st.count, 32, 0, e->stream>>>(c);
+  } else {
+    if (!st.leaf) {
+      const size_t needDesc = (size_t)st.count * tilesS;
+      c.descA = e->dDesc;
+      c.descB = e->dDesc + needDesc;
+      c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + 2 * needDesc);
+      CK(cudaMemsetAsync(e->dDesc, 0, (2 * needDesc + 1) * sizeof(unsigned long long), e->stream));
+      ProfScope p(e, DCSMC_K_SCAN);
+      k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, e->stream>>>(c, tilesS);
+    }
     ProfScope p(e, DCSMC_K_FINALIZE);
     k_finalize<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
   }
-  if (!st.leaf) {
+  if (!st.leaf || javaSums) {
     const int tilesT = (c.invB + 1 + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
     ProfScope p(e, DCSMC_K_RESAMPLE);
     k_build_inverse_table<<<(unsigned)(st.count * tilesT), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesT);
@@ -647,6 +653,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.cdf = e->dCdf;
   c.invTable = e->dInvTable;
   c.invB = e->invB;
+  c.javaSums = e->opt.sumMode == DCSMC_SUM_JAVA;
   c.uniformLogW = uniformLeafLogW(e);
   return DCSMC_OK;
 }
@@ -676,7 +683,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   size_t maxStep = 0, maxInternalStep = 0;
   for (auto& s : plan.steps) {
     maxStep = std::max<size_t>(maxStep, s.count);
-    if (!s.leaf) maxInternalStep = std::max<size_t>(maxInternalStep, s.count);
+    if (!s.leaf || e->opt.sumMode == DCSMC_SUM_JAVA) maxInternalStep = std::max<size_t>(maxInternalStep, s.count);
   }
   const size_t tilesS = (N + SCAN_TILE - 1) / SCAN_TILE;
   auto grow = [&](void** p, size_t& cap, size_t need, size_t elem) -> cudaError_t {
@@ -873,8 +880,8 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
     g_createError = "maxBetaAttempts must be >= 1";
     return DCSMC_EINVAL;
   }
-  if (opt->sumMode != DCSMC_SUM_EXACT) {
-    g_createError = "only DCSMC_SUM_EXACT is implemented";
+  if (opt->sumMode != DCSMC_SUM_EXACT && opt->sumMode != DCSMC_SUM_JAVA) {
+    g_createError = "sumMode must be DCSMC_SUM_EXACT or DCSMC_SUM_JAVA";
     return DCSMC_EINVAL;
   }
   int nDev = 0;

@@ -198,3 +198,45 @@ def test_device_elementary_functions_equal_fdlibm_oracle():
         ud = e.debug_eval(2 | (7 << 8), idx)
         uo = np.array([L.orc_philox_uniform(31, 7, int(i)) for i in idx])
         assert np.array_equal(ud, uo)
+
+
+@pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
+@pytest.mark.parametrize("threshold", [1.0 + 1e-10, 0.5])
+def test_java_order_sums_bit_exact_against_java_order_oracle(scheme, threshold):
+    """DCSMC_SUM_JAVA: the device runs the reference's own summation order (sequential fp64 S, W_i =
+    e_i/S, compensated sum of squares, running-sum CDF, unscaled darts). Against the oracle in
+    java-order mode everything is bit-identical — no 'device-order' caveat at all."""
+    csr, nT, nS = small_dataset(seed=13)
+    N = 3000
+    ref = o.run(csr, N, masterRandomSeed=31, resamplingScheme=scheme, relativeEssThreshold=threshold,
+                rngMode=o.RNG_PHILOX, sumMode=o.SUM_JAVA, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+    with Engine(nParticles=N, masterRandomSeed=31, resamplingScheme=scheme, relativeEssThreshold=threshold,
+                sumMode=1, retainPopulations=1) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        compare_all(e, ref, csr)
+        rs, _, rw = e.population(0)
+        assert np.array_equal(rs, ref.rootState, equal_nan=True)
+        assert np.array_equal(rw, ref.rootWeights)
+
+
+def test_gpu_reproduces_the_reference_recorded_run_to_every_digit():
+    """The reference's only golden vector (Doc.java:282 = README.md:257), on the GPU:
+    nParticles=1e6, masterRandomSeed=31, MULTINOMIAL, relativeEssThreshold=0.5, perfect binary tree
+    of depth 3. java.util.Random regenerated on the device (DCSMC_RNG_JAVA) + the reference's
+    summation order (DCSMC_SUM_JAVA) give
+        ESS=548622.6672945316, rESS=0.5486226672945316, logZ=-3.5950250310183574."""
+    csr = d.perfectBinaryTree(3).to_csr()
+    with Engine(nParticles=1_000_000, masterRandomSeed=31, resamplingScheme=0, relativeEssThreshold=0.5,
+                rngMode=2, sumMode=1) as e:
+        e.set_tree(csr)
+        e.set_markov_model(T, PRIOR)
+        e.run()
+        root = e.node_stats(0)
+        assert root.logNormEstimate == -3.5950250310183574
+        assert root.ess == 548622.6672945316
+        assert root.relEss == 0.5486226672945316
+        names = [n.toString() for n in csr.nodes]
+        st = e.all_node_stats()
+        assert sorted(names[i] for i in np.nonzero(st["resampled"])[0]) == ["0-0", "0-1"]
