@@ -162,10 +162,17 @@ int slotsPerParticle(const dcsmc_engine* e, int n) {
 
 size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Observed (Gaussian) leaves hold N copies of one datum: unless populations are retained for
+// inspection (or the parity mode wants every array) they get no slot and no kernel work.
+bool skipObservedLeaves(const dcsmc_engine* e) {
+  return e->model == DCSMC_MODEL_MULTILEVEL && !e->opt.retainPopulations && e->opt.sumMode == DCSMC_SUM_EXACT;
+}
+
 // bytes of one node's resident population. Leaves carry no log-weight column (all equal).
 size_t slotBytes(const dcsmc_engine* e, int n) {
   const size_t NP = (size_t)e->Npad;
   const bool internal = nodeKind(e, n) == KIND_INTERNAL || (!e->imported.empty() && e->imported[n]);
+  if (!internal && nodeKind(e, n) == KIND_LEAF_GAUSS && skipObservedLeaves(e)) return 0;
   size_t b = 0;
   if (e->model == DCSMC_MODEL_MARKOV) {
     b = NP * 4 /*istate*/ + NP * 4 /*anc*/ + (internal ? NP * 8 : 0) /*logw*/;
@@ -183,6 +190,11 @@ void poolFree(dcsmc_engine* e, int n);
 bool poolAlloc(dcsmc_engine* e, int n) {
   poolFree(e, n);  // recomputing a node reuses nothing of its old population
   const size_t b = slotBytes(e, n);
+  if (b == 0) {
+    e->slot[n] = Slot{0, 0};
+    e->resident[n] = 1;
+    return true;
+  }
   auto best = e->freeBySize.end();
   for (auto it = e->freeBySize.begin(); it != e->freeBySize.end(); ++it)
     if (it->second >= b && (best == e->freeBySize.end() || it->second < best->second)) best = it;
@@ -213,6 +225,7 @@ void poolFree(dcsmc_engine* e, int n) {
   if (!e->resident[n]) return;
   e->resident[n] = 0;
   size_t off = e->slot[n].offset, len = e->slot[n].bytes;
+  if (len == 0) return;
   auto next = e->freeBySize.lower_bound(off);
   if (next != e->freeBySize.begin()) {
     auto prev = std::prev(next);
@@ -654,6 +667,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.invTable = e->dInvTable;
   c.invB = e->invB;
   c.javaSums = e->opt.sumMode == DCSMC_SUM_JAVA;
+  c.skipObs = skipObservedLeaves(e);
   c.uniformLogW = uniformLeafLogW(e);
   return DCSMC_OK;
 }

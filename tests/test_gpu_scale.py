@@ -130,3 +130,44 @@ def test_nys_config1_matches_oracle_statistics():
                 nThreads=8, maximumDistributionDepth=2)
     assert np.allclose(st["logNormEstimate"], lit.logNormEstimate, rtol=1e-9, atol=1e-9)
     assert np.allclose(st["ess"], lit.ess, rtol=1e-9)
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_observed_leaves_not_materialised_same_results(scheme):
+    """Observed (Gaussian) leaves are N copies of one datum; without retainPopulations they get no
+    slot and no kernel work. Every node statistic and the root population must still equal the
+    oracle's (which does materialise and resample them) — also when binomial and observed leaves
+    share a parent."""
+    csr, leafKind, leafObs = synth.binary_gauss_tree(6)
+    N = 3000
+    ref = o.run(csr, N, resamplingScheme=scheme, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM,
+                leafKind=leafKind, leafObs=leafObs)
+    with Engine(nParticles=N, resamplingScheme=scheme) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(leafKind=leafKind, leafObs=leafObs)
+        e.run()
+        st = e.all_node_stats()
+        for k in ("ess", "relEss", "logNormEstimate", "logScaling", "resampled"):
+            assert np.array_equal(st[k], getattr(ref, k)), k
+        rs, _, rw = e.population(0)
+        assert np.array_equal(rs, ref.rootState, equal_nan=True)
+    # mixed leaves
+    csr, nT, nS = dataset(synth.small_multilevel_rows(seed=2))
+    leafKind = np.zeros(csr.nNodes, np.int32)
+    leafObs = np.zeros(csr.nNodes)
+    leaves = [i for i in range(csr.nNodes) if csr.nChildren(i) == 0]
+    for i in leaves[::2]:
+        leafKind[i] = 1
+        leafObs[i] = 0.1 * i - 0.7
+    ref = o.run(csr, N, resamplingScheme=scheme, relativeEssThreshold=0.7, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, leafKind=leafKind, leafObs=leafObs)
+    with Engine(nParticles=N, resamplingScheme=scheme, relativeEssThreshold=0.7) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS, leafKind, leafObs)
+        e.run()
+        st = e.all_node_stats()
+        for k in ("ess", "logNormEstimate", "resampled"):
+            assert np.array_equal(st[k], getattr(ref, k)), k
+        rs, _, rw = e.population(0)
+        assert np.array_equal(rs, ref.rootState, equal_nan=True)
+        assert np.array_equal(rw, ref.rootWeights)
