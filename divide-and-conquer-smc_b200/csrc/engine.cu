@@ -110,6 +110,7 @@ struct dcsmc_engine {
   size_t invTableCap = 0;
   int invB = 1;
   size_t leafSmemSet[3] = {0, 0, 0};
+  size_t smallSmemSet[3] = {0, 0, 0};
   std::vector<CachedPlan> planCache;
   const CachedPlan* devicePlan = nullptr;  // whose descriptors are currently uploaded
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
@@ -583,6 +584,19 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   } else {
     ProfScope p(e, DCSMC_K_INTERNAL);
     k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
+  }
+  const bool smallNode = !st.leaf && !javaSums && N <= SMALLN_MAX;
+  if (smallNode) {
+    // the population fits in shared memory: one block per node does everything after propose
+    const size_t smem = smalln_smem_bytes(c.Npad);
+    if (smem > e->smallSmemSet[RNG]) {
+      CK(cudaFuncSetAttribute(k_node_small<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      e->smallSmemSet[RNG] = smem;
+    }
+    ProfScope p(e, DCSMC_K_SCAN);
+    k_node_small<RNG><<<st.count, SMALLN_THREADS, smem, e->stream>>>(c);
+    CK(cudaGetLastError());
+    return DCSMC_OK;
   }
   if (st.leaf) {
     // all weights equal: the exact sums are known in closed form, no scan and no CDF
