@@ -37,6 +37,7 @@ struct Step {
 struct Slot {
   size_t offset = 0;
   size_t bytes = 0;
+  char* external = nullptr;  // unpacked populations live in their own allocation, not in the pool
 };
 
 struct Plan {
@@ -53,7 +54,7 @@ struct CachedPlan {
   size_t poolTop = 0;
   std::vector<Slot> slot;
   std::vector<char> resident, imported;
-  bool uploaded = false;  // this plan's step lists / node descriptors are the ones on the device
+  std::vector<char> inPlan;  // per node: computed by this plan
 };
 
 }  // namespace
@@ -81,8 +82,11 @@ struct dcsmc_engine {
   NodeStats* dStats = nullptr;
   LeafConst* dLeaf = nullptr;
   int32_t* dChildren = nullptr;
-  int32_t* dStepNodes = nullptr;
+  int32_t* dStepNodes = nullptr;     // step lists of the cached plan `devicePlan`
   size_t stepNodesCap = 0;
+  int32_t* dStepNodesTmp = nullptr;  // step lists of the current uncached plan
+  size_t stepNodesTmpCap = 0;
+  int32_t* curStepNodes = nullptr;   // the one the running plan uses
   double** dInj = nullptr;
   uint64_t* dJavaState = nullptr;
   double *dMarkovT = nullptr, *dMarkovPrior = nullptr;
@@ -92,13 +96,19 @@ struct dcsmc_engine {
   char* pool = nullptr;
   size_t poolBytes = 0;
   bool poolIsBudget = false;  // pool was capped by the memory budget
+  size_t poolNeed = 0;        // bytes of "everything resident at once" (0 = not computed yet)
   std::map<size_t, size_t> freeBySize;  // free holes below poolTop: offset -> bytes (coalesced)
   size_t poolTop = 0;
   std::vector<Slot> slot;        // per node
   std::vector<char> resident;    // per node
   std::vector<char> imported;    // per node: population installed by dcsmc_population_unpack
+  std::vector<char*> importFree;  // recycled buffers of unpacked populations (all the same size)
+  struct Undo { int node; Slot slot; char resident, imported; };
+  std::vector<Undo> undo;         // per-node pool changes since the planner's last checkpoint
+  bool undoOn = false;
   std::vector<NodeDev> hNodes;   // host mirror
   std::vector<dcsmc_node_stats_t> hStats;
+  std::vector<NodeStats> hStatsRaw;  // host staging of the device statistics table
   int Npad = 0;
 
   // scratch
@@ -113,6 +123,7 @@ struct dcsmc_engine {
   size_t smallSmemSet[3] = {0, 0, 0};
   std::vector<CachedPlan> planCache;
   const CachedPlan* devicePlan = nullptr;  // whose descriptors are currently uploaded
+  std::vector<int> descDirty;              // nodes whose device descriptor was rewritten since then
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
   size_t offspringCap = 0;
 
@@ -172,7 +183,7 @@ bool skipObservedLeaves(const dcsmc_engine* e) {
 // bytes of one node's resident population. Leaves carry no log-weight column (all equal).
 size_t slotBytes(const dcsmc_engine* e, int n) {
   const size_t NP = (size_t)e->Npad;
-  const bool internal = nodeKind(e, n) == KIND_INTERNAL || (!e->imported.empty() && e->imported[n]);
+  const bool internal = nodeKind(e, n) == KIND_INTERNAL;
   if (!internal && nodeKind(e, n) == KIND_LEAF_GAUSS && skipObservedLeaves(e)) return 0;
   size_t b = 0;
   if (e->model == DCSMC_MODEL_MARKOV) {
@@ -188,8 +199,15 @@ void poolFree(dcsmc_engine* e, int n);
 // Population pool: a bump pointer (poolTop) plus coalesced free holes below it. Best fit over the
 // holes first, then the hole touching poolTop is extended, then fresh space. All of this runs at
 // plan time on the host; the device only ever sees final addresses.
+// bytes of an unpacked population: always the internal layout (6 columns + ancestors + logw)
+size_t importBytes(const dcsmc_engine* e) {
+  const size_t NP = (size_t)e->Npad;
+  return alignUp(e->model == DCSMC_MODEL_MARKOV ? NP * 16 : NP * 60, 256);
+}
+
 bool poolAlloc(dcsmc_engine* e, int n) {
   poolFree(e, n);  // recomputing a node reuses nothing of its old population
+  if (e->undoOn) e->undo.push_back({n, e->slot[n], e->resident[n], e->imported[n]});
   const size_t b = slotBytes(e, n);
   if (b == 0) {
     e->slot[n] = Slot{0, 0};
@@ -224,7 +242,14 @@ bool poolAlloc(dcsmc_engine* e, int n) {
 
 void poolFree(dcsmc_engine* e, int n) {
   if (!e->resident[n]) return;
+  if (e->undoOn) e->undo.push_back({n, e->slot[n], e->resident[n], e->imported[n]});
   e->resident[n] = 0;
+  if (e->slot[n].external) {  // unpacked population: recycle its buffer
+    e->importFree.push_back(e->slot[n].external);
+    e->slot[n].external = nullptr;
+    e->imported[n] = 0;
+    return;
+  }
   size_t off = e->slot[n].offset, len = e->slot[n].bytes;
   if (len == 0) return;
   auto next = e->freeBySize.lower_bound(off);
@@ -249,7 +274,7 @@ void poolFree(dcsmc_engine* e, int n) {
 void fillNodeDev(dcsmc_engine* e, int n) {
   NodeDev& d = e->hNodes[n];
   const size_t NP = (size_t)e->Npad;
-  char* base = e->pool + e->slot[n].offset;
+  char* base = e->slot[n].external ? e->slot[n].external : e->pool + e->slot[n].offset;
   d.childBegin = e->childOffsets[n];
   d.nChildren = nChildrenOf(e, n);
   d.kind = nodeKind(e, n);
@@ -353,7 +378,13 @@ int uploadTables(dcsmc_engine* e) {
   CK(cudaStreamSynchronize(e->stream));
   e->hNodes.assign(nN, NodeDev{});
   e->hStats.assign(nN, dcsmc_node_stats_t{});
+  for (Slot& sl : e->slot)  // buffers of unpacked populations (their size depends on the model)
+    if (sl.external) cudaFree(sl.external);
+  for (char* p : e->importFree) cudaFree(p);
+  e->importFree.clear();
   e->slot.assign(nN, Slot{});
+  e->poolNeed = 0;
+  e->descDirty.clear();
   e->planCache.clear();
   e->devicePlan = nullptr;
   e->resident.assign(nN, 0);
@@ -385,8 +416,9 @@ int uploadInjected(dcsmc_engine* e) {
 
 int ensurePool(dcsmc_engine* e) {
   // the pool never needs more than "everything resident at once"
-  size_t all = 0;
-  for (int n = 0; n < e->nNodes; ++n) all += slotBytes(e, n);
+  if (e->poolNeed == 0)
+    for (int n = 0; n < e->nNodes; ++n) e->poolNeed += slotBytes(e, n);
+  const size_t all = std::max<size_t>(e->poolNeed, 256);
   if (e->pool && (e->poolBytes >= all || e->poolIsBudget)) return DCSMC_OK;
   if (e->pool) {
     cudaFree(e->pool);
@@ -449,21 +481,38 @@ bool emitLevels(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan, bool
   return true;
 }
 
+// Planner checkpoint: the free-hole map is small and copied; per-node arrays are rolled back from
+// the undo log (copying them per trial would cost O(nNodes) even for a one-node plan).
 struct PoolState {
   std::map<size_t, size_t> freeBySize;
   size_t poolTop;
-  std::vector<Slot> slot;
-  std::vector<char> resident, imported;
+  size_t undoMark;
+  bool undoWasOn;
 };
-PoolState savePool(const dcsmc_engine* e) {
-  return PoolState{e->freeBySize, e->poolTop, e->slot, e->resident, e->imported};
+PoolState savePool(dcsmc_engine* e) {
+  PoolState s{e->freeBySize, e->poolTop, e->undo.size(), e->undoOn};
+  e->undoOn = true;
+  return s;
 }
 void restorePool(dcsmc_engine* e, const PoolState& s) {
   e->freeBySize = s.freeBySize;
   e->poolTop = s.poolTop;
-  e->slot = s.slot;
-  e->resident = s.resident;
-  e->imported = s.imported;
+  while (e->undo.size() > s.undoMark) {
+    const dcsmc_engine::Undo& u = e->undo.back();
+    if (u.slot.external) {  // the trial recycled this unpacked population's buffer: take it back
+      auto it = std::find(e->importFree.begin(), e->importFree.end(), u.slot.external);
+      if (it != e->importFree.end()) e->importFree.erase(it);
+    }
+    e->slot[u.node] = u.slot;
+    e->resident[u.node] = u.resident;
+    e->imported[u.node] = u.imported;
+    e->undo.pop_back();
+  }
+  e->undoOn = s.undoWasOn;
+}
+void commitPool(dcsmc_engine* e, const PoolState& s) {
+  e->undoOn = s.undoWasOn;
+  if (!e->undoOn) e->undo.clear();
 }
 
 // Memory-aware recursive planner: try the whole root set level by level; if the pool
@@ -478,6 +527,7 @@ int planRoots(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan) {
     if (emitLevels(e, roots, trial, false, peak)) {
       for (auto& s : trial.steps) plan.steps.push_back(std::move(s));
       plan.stepNodes = std::move(trial.stepNodes);
+      commitPool(e, saved);
       return DCSMC_OK;
     }
     restorePool(e, saved);
@@ -547,7 +597,7 @@ double uniformLeafLogW(const dcsmc_engine* e) {
 template <int RNG>
 int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   RunCtx c = base;
-  c.stepNodes = e->dStepNodes + st.offset;
+  c.stepNodes = e->curStepNodes + st.offset;
   c.nStepNodes = st.count;
   const int N = c.N;
   const int tilesP = (N + PROPOSE_THREADS - 1) / PROPOSE_THREADS;
@@ -734,25 +784,50 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   CK(grow((void**)&e->dInvTable, e->invTableCap, std::max<size_t>(1, maxInternalStep * ((size_t)e->invB + 1)), sizeof(int32_t)));
   if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL)
     CK(grow((void**)&e->dOffspring, e->offspringCap, maxStep * (size_t)e->Npad, sizeof(int32_t)));
-  const bool descriptorsOnDevice = cached != nullptr && e->devicePlan == cached;
-  if (!descriptorsOnDevice) {
-    if (plan.stepNodes.size() > e->stepNodesCap) {
-      if (e->dStepNodes) cudaFree(e->dStepNodes);
-      e->dStepNodes = nullptr;
-      CK(cudaMalloc((void**)&e->dStepNodes, plan.stepNodes.size() * sizeof(int32_t)));
-      e->stepNodesCap = plan.stepNodes.size();
+  bool descriptorsOnDevice = cached != nullptr && e->devicePlan == cached;
+  if (descriptorsOnDevice) {
+    // other plans / unpack may have rewritten descriptors since; they only matter if they hit this plan
+    for (int n : e->descDirty)
+      if (cached->inPlan[n]) {
+        descriptorsOnDevice = false;
+        break;
+      }
+  }
+  if (cached != nullptr) e->descDirty.clear();
+  {
+    int32_t*& buf = cached ? e->dStepNodes : e->dStepNodesTmp;
+    size_t& cap = cached ? e->stepNodesCap : e->stepNodesTmpCap;
+    if (plan.stepNodes.size() > cap) {
+      if (buf) cudaFree(buf);
+      buf = nullptr;
+      CK(cudaMalloc((void**)&buf, plan.stepNodes.size() * sizeof(int32_t)));
+      cap = plan.stepNodes.size();
+      descriptorsOnDevice = false;
     }
-    CK(cudaMemcpyAsync(e->dStepNodes, plan.stepNodes.data(), plan.stepNodes.size() * sizeof(int32_t),
-                       cudaMemcpyHostToDevice, e->stream));
-    // node descriptors for every node touched by the plan
+    e->curStepNodes = buf;
+    if (!descriptorsOnDevice)
+      CK(cudaMemcpyAsync(buf, plan.stepNodes.data(), plan.stepNodes.size() * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, e->stream));
+  }
+  if (!descriptorsOnDevice) {
+    // node descriptors for every node touched by the plan (a few nodes: one small copy each;
+    // otherwise the whole table)
     for (int n : plan.stepNodes) fillNodeDev(e, n);
-    CK(cudaMemcpyAsync(e->dNodes, e->hNodes.data(), sizeof(NodeDev) * e->nNodes, cudaMemcpyHostToDevice, e->stream));
-    e->devicePlan = cached;
+    if (plan.stepNodes.size() * 16 < (size_t)e->nNodes) {
+      for (int n : plan.stepNodes) {
+        CK(cudaMemcpyAsync(e->dNodes + n, &e->hNodes[n], sizeof(NodeDev), cudaMemcpyHostToDevice, e->stream));
+        if (cached == nullptr) e->descDirty.push_back(n);
+      }
+    } else {
+      if (cached == nullptr) e->devicePlan = nullptr;  // a large uncached plan: just re-upload next time
+      CK(cudaMemcpyAsync(e->dNodes, e->hNodes.data(), sizeof(NodeDev) * e->nNodes, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (cached != nullptr) e->devicePlan = cached;
   }
   // accumulators of the nodes about to be recomputed start from zero
   if (!plan.stepNodes.empty()) {
     const int n = (int)plan.stepNodes.size();
-    k_reset_stats<<<(n + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->dStepNodes, n);
+    k_reset_stats<<<(n + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->curStepNodes, n);
     CK(cudaGetLastError());
   }
   RunCtx c;
@@ -780,15 +855,23 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     }
   }
   CK(cudaEventRecord(e->ev1, e->stream));
-  // fetch stats of all nodes (small)
-  std::vector<NodeStats> hs(e->nNodes);
-  CK(cudaMemcpyAsync(hs.data(), e->dStats, sizeof(NodeStats) * e->nNodes, cudaMemcpyDeviceToHost, e->stream));
+  // fetch the statistics of the nodes this plan computed
+  const bool fewNodes = plan.stepNodes.size() * 16 < (size_t)e->nNodes;
+  if ((int)e->hStatsRaw.size() != e->nNodes) e->hStatsRaw.assign(e->nNodes, NodeStats{});
+  std::vector<NodeStats>& hs = e->hStatsRaw;
+  if (fewNodes) {
+    for (int n : plan.stepNodes)
+      CK(cudaMemcpyAsync(&hs[n], e->dStats + n, sizeof(NodeStats), cudaMemcpyDeviceToHost, e->stream));
+    e->info.d2hBytes = (int64_t)(sizeof(NodeStats) * plan.stepNodes.size());
+  } else {
+    CK(cudaMemcpyAsync(hs.data(), e->dStats, sizeof(NodeStats) * e->nNodes, cudaMemcpyDeviceToHost, e->stream));
+  }
   CK(cudaStreamSynchronize(e->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->info.deviceMs = ms;
   e->info.particleUpdates = e->info.nodesProcessed * (int64_t)N;
-  for (int n = 0; n < e->nNodes; ++n) {
+  for (int n : plan.stepNodes) {
     dcsmc_node_stats_t& o = e->hStats[n];
     o.ess = hs[n].ess;
     o.relEss = hs[n].relEss;
@@ -855,10 +938,11 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
     cp.slot = e->slot;
     cp.resident = e->resident;
     cp.imported = e->imported;
+    cp.inPlan.assign(e->nNodes, 0);
+    for (int n : plan.stepNodes) cp.inPlan[n] = 1;
     e->planCache.push_back(std::move(cp));
     return executePlan(e, e->planCache.back().plan, &e->planCache.back());
   }
-  e->devicePlan = nullptr;
   return executePlan(e, plan);
 }
 
@@ -937,7 +1021,10 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (double* p : e->injDev)
     if (p) cudaFree(p);
-  void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dInj, e->dJavaState,
+  for (Slot& sl : e->slot)
+    if (sl.external) cudaFree(sl.external);
+  for (char* p : e->importFree) cudaFree(p);
+  void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dStepNodesTmp, e->dInj, e->dJavaState,
                   e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1096,7 +1183,11 @@ int32_t dcsmc_node_stats(const dcsmc_engine* e, int32_t node, dcsmc_node_stats_t
 
 int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out) {
   if (!e || !out) return DCSMC_EINVAL;
-  if ((int)e->hStats.size() != e->nNodes) return e->fail(DCSMC_ESTATE, "no run yet");
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
+  if ((int)e->hStats.size() != e->nNodes) {  // nothing computed on this engine yet: done == 0 everywhere
+    memset(out, 0, sizeof(dcsmc_node_stats_t) * e->nNodes);
+    return DCSMC_OK;
+  }
   memcpy(out, e->hStats.data(), sizeof(dcsmc_node_stats_t) * e->nNodes);
   return DCSMC_OK;
 }
@@ -1233,13 +1324,18 @@ int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* devic
   if (h.magic != PACK_MAGIC || h.N != e->opt.nParticles || h.model != (e->model == DCSMC_MODEL_MARKOV ? 1 : 0))
     return e->fail(DCSMC_EINVAL, "packed population does not match this engine (magic/N/model)");
   poolFree(e, node);
-  e->imported[node] = 1;
-  if (!poolAlloc(e, node)) {
-    e->imported[node] = 0;
-    return e->fail(DCSMC_ENOMEM, "population pool (%zu bytes) cannot hold the unpacked node %d", e->poolBytes, node);
+  char* buf = nullptr;
+  if (!e->importFree.empty()) {
+    buf = e->importFree.back();
+    e->importFree.pop_back();
+  } else {
+    CK(cudaMalloc((void**)&buf, importBytes(e)));
   }
+  e->slot[node] = Slot{0, 0, buf};
+  e->resident[node] = 1;
+  e->imported[node] = 1;
   fillNodeDev(e, node);
-  e->devicePlan = nullptr;
+  e->descDirty.push_back(node);
   CK(cudaMemcpyAsync(e->dNodes + node, &e->hNodes[node], sizeof(NodeDev), cudaMemcpyHostToDevice, e->stream));
   RunCtx c;
   makeCtx(e, c);
@@ -1260,6 +1356,11 @@ int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* devic
 
 int32_t dcsmc_reset_populations(dcsmc_engine* e) {
   if (!e) return DCSMC_EINVAL;
+  for (size_t n = 0; n < e->slot.size(); ++n)
+    if (e->slot[n].external) {
+      e->importFree.push_back(e->slot[n].external);
+      e->slot[n].external = nullptr;
+    }
   std::fill(e->resident.begin(), e->resident.end(), 0);
   std::fill(e->imported.begin(), e->imported.end(), 0);
   for (auto& s : e->hStats) s = dcsmc_node_stats_t{};

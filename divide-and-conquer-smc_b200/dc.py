@@ -279,7 +279,7 @@ class DistributedDC:
         self.csr = tree.to_csr()
         self.device = device
         self.engine: Optional[Engine] = None
-        self.stats: Optional[Dict[str, np.ndarray]] = None
+        self._stats: Optional[Dict[str, np.ndarray]] = None
         self.nWorkers = 1
         self.nodeTimeMs: Dict[Any, float] = {}
         self.globalTimeMs = 0.0
@@ -329,9 +329,9 @@ class DistributedDC:
             self.engine = self._make_engine()
         dist = self._dist()
         t0 = time.perf_counter()
+        self._stats = None  # gathered lazily (a collective when sharded): see `stats`
         if dist is None:
             self.engine.run()
-            self.stats = self.engine.all_node_stats()
             info = self.engine.run_info()
             self.lastRun = dict(deviceMs=info.deviceMs, kernelLaunches=info.kernelLaunches,
                                 particleUpdates=info.particleUpdates, algorithmicBytes=info.algorithmicBytes,
@@ -410,19 +410,37 @@ class DistributedDC:
             if my_nodes:
                 e.run_nodes(my_nodes)
                 account()
-        # every rank learns every node's statistics (each node was computed on exactly one rank)
-        st = e.all_node_stats()
-        keys = ["ess", "relEss", "logNormEstimate", "logScaling"]
-        mat = np.stack([np.where(own == rank, st[k], 0.0) for k in keys] + [np.where(own == rank, st["resampled"], 0).astype(np.float64)])
-        tens = torch.from_numpy(mat).to(dev)
-        dist.all_reduce(tens)
-        mat = tens.cpu().numpy()
-        self.stats = {k: mat[i] for i, k in enumerate(keys)}
-        self.stats["resampled"] = mat[4].astype(np.int32)
-        self.stats["done"] = np.ones(self.csr.nNodes, np.int32)
         self.rootOwner = plan.node_owner[0]
         self.lastRun = dict(deviceMs=devms, kernelLaunches=launches, particleUpdates=updates, algorithmicBytes=algbytes,
                             h2dBytes=0, d2hBytes=0, nvlinkBytes=nvbytes)
+
+    @property
+    def stats(self) -> Dict[str, np.ndarray]:
+        """Per-node ESS / rESS / logNormEstimate / logScaling / resampled of the last run. Sharded runs:
+        every node was computed on exactly one rank, so this is an all-reduce — a collective that
+        every rank must call (start() does)."""
+        if self._stats is not None:
+            return self._stats
+        st = self.engine.all_node_stats()
+        dist = self._dist()
+        if dist is None:
+            self._stats = st
+            return st
+        import torch
+
+        rank = dist.get_rank()
+        own = self._nodeOwner
+        keys = ["ess", "relEss", "logNormEstimate", "logScaling"]
+        mat = np.stack([np.where(own == rank, st[k], 0.0) for k in keys] + [np.where(own == rank, st["resampled"], 0).astype(np.float64)])
+        dev = torch.device("cuda", self.engine.options.device) if torch.cuda.is_available() else torch.device("cpu")
+        tens = torch.from_numpy(mat).to(dev)
+        dist.all_reduce(tens)
+        mat = tens.cpu().numpy()
+        out = {k: mat[i] for i, k in enumerate(keys)}
+        out["resampled"] = mat[4].astype(np.int32)
+        out["done"] = np.ones(self.csr.nNodes, np.int32)
+        self._stats = out
+        return out
 
     def _population_view(self, i: int, fetch=None) -> ParticlePopulation:
         st = self.stats

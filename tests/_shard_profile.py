@@ -8,9 +8,17 @@ from dcsmc_b200 import synth, dc as dcmod
 local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 rank = dist.get_rank()
-ds = d.MultiLevelDataset(rows=synth.nys_shaped_rows())
-opt = d.DCOptions(nParticles=100000, maximumDistributionDepth=2)
-ddc = d.DistributedDC.createInstance(opt, d.MultiLevelProposalFactory(dataset=ds), ds.getTree(), device=local)
+if len(sys.argv) > 1 and sys.argv[1] == "binary16":
+    tree = d.perfectBinaryTree(16); csr = tree.to_csr()
+    import numpy as np
+    rng = np.random.default_rng(4)
+    obs = {n: float(rng.normal()) for i, n in enumerate(csr.nodes) if csr.nChildren(i) == 0}
+    opt = d.DCOptions(nParticles=10000, maximumDistributionDepth=3)
+    ddc = d.DistributedDC.createInstance(opt, d.GaussianLeafProposalFactory(obs), tree, device=local)
+else:
+    ds = d.MultiLevelDataset(rows=synth.nys_shaped_rows())
+    opt = d.DCOptions(nParticles=100000, maximumDistributionDepth=2)
+    ddc = d.DistributedDC.createInstance(opt, d.MultiLevelProposalFactory(dataset=ds), ds.getTree(), device=local)
 for _ in range(3): ddc.run()
 # monkeypatch timers
 E = ddc.engine

@@ -27,6 +27,8 @@ def main():
     for scheme in (d.ResamplingScheme.MULTINOMIAL, d.ResamplingScheme.STRATIFIED):
         for thr in (1.0 + 1e-10, 0.6):
             for depth in (1, 2, 2 ** 31 - 1):
+                if os.environ.get("DCSMC_CHECK_VERBOSE"):
+                    print(f"[rank {rank}] scheme={int(scheme)} thr={thr} depth={depth}", flush=True)
                 opt = d.DCOptions(nParticles=N, resamplingScheme=scheme, relativeEssThreshold=thr, maximumDistributionDepth=depth)
                 ddc = d.DistributedDC.createInstance(opt, d.MultiLevelProposalFactory(dataset=ds), ds.getTree(), device=local)
                 ddc.start()

@@ -133,7 +133,7 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_sharded_run_is_bit_identical_to_single_gpu(world):
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
