@@ -62,8 +62,13 @@ struct CachedPlan {
 struct dcsmc_engine {
   dcsmc_options opt{};
   mutable std::string err;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // launching stream: propose kernels, copies, timing events
+  cudaStream_t streamR = nullptr;  // higher priority: the normalise/resample chain of a level chunk
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> evPool;  // untimed events ordering the two streams
+  size_t evNext = 0;
+  int smCount = 148;
+  int overlapChunks = 1;            // level batches are split in this many chunks (1 = one stream)
 
   // topology / model (host)
   int nNodes = 0, root = 0;
@@ -124,6 +129,8 @@ struct dcsmc_engine {
   std::vector<CachedPlan> planCache;
   const CachedPlan* devicePlan = nullptr;  // whose descriptors are currently uploaded
   std::vector<int> descDirty;              // nodes whose device descriptor was rewritten since then
+  char *dStage = nullptr, *hStage = nullptr;  // dcsmc_population_copy_to_host staging (device / pinned host)
+  size_t stageCap = 0;
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
   size_t offspringCap = 0;
 
@@ -572,17 +579,18 @@ struct ProfScope {
   dcsmc_engine* e;
   int cls;
   cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(dcsmc_engine* e_, int cls_) : e(e_), cls(cls_) {
+  cudaStream_t s;
+  ProfScope(dcsmc_engine* e_, int cls_, cudaStream_t s_) : e(e_), cls(cls_), s(s_) {
     e->info.kernelLaunches++;
     if (e->profile) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, e->stream);
+      cudaEventRecord(a, s);
     }
   }
   ~ProfScope() {
     if (e->profile) {
-      cudaEventRecord(b, e->stream);
+      cudaEventRecord(b, s);
       e->profEvents.push_back({cls, {a, b}});
     }
   }
@@ -594,15 +602,49 @@ double uniformLeafLogW(const dcsmc_engine* e) {
   return dc_log(1.0) + 0.0;  // MultiLevelLeafProposal.java:40
 }
 
+// Two-stream pipeline of a level batch. The propose kernels are fp64/issue bound and leave the
+// memory system idle; the chain after them (scan, table, darts, expansion) is L2/latency bound and
+// leaves the issue slots idle. A level is therefore cut into chunks of nodes: chunk k's chain runs
+// on the high-priority stream while chunk k+1's propose kernel runs on the launching stream.
+// Scratch (CDF, offspring counts, inverse tables, look-back descriptors) is indexed by the node's
+// position in the level, so chunks use disjoint regions.
+struct ChunkCtx {
+  cudaStream_t sP, sR;   // propose stream, chain stream (== sP when not overlapping)
+  int lo;                // first node of the chunk inside its level batch
+  int idx;               // chunk number inside the level batch
+};
+
+cudaEvent_t nextEvent(dcsmc_engine* e) {
+  if (e->evNext == e->evPool.size()) {
+    cudaEvent_t ev = nullptr;
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    e->evPool.push_back(ev);
+  }
+  return e->evPool[e->evNext++];
+}
+
+// look-back descriptor words per node of a step (scan: A and B limbs; expansion: one)
+size_t descWordsPerNode(int N) {
+  const size_t tilesS = (N + SCAN_TILE - 1) / SCAN_TILE, tilesE = (N + EXPAND_TILE - 1) / EXPAND_TILE;
+  return std::max(2 * tilesS, tilesE);
+}
+constexpr int MAX_CHUNKS = 16;
+
 template <int RNG>
-int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
+int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkCtx& ch) {
   RunCtx c = base;
   c.stepNodes = e->curStepNodes + st.offset;
   c.nStepNodes = st.count;
   const int N = c.N;
+  const cudaStream_t sP = ch.sP, sR = ch.sR;
+  // this chunk's scratch
+  c.cdf = e->dCdf ? e->dCdf + (size_t)ch.lo * c.Npad : nullptr;
+  c.invTable = e->dInvTable ? e->dInvTable + (size_t)ch.lo * (c.invB + 1) : nullptr;
+  int32_t* const offspring = e->dOffspring ? e->dOffspring + (size_t)ch.lo * c.Npad : nullptr;
+  unsigned long long* const desc = e->dDesc + (size_t)ch.lo * descWordsPerNode(N) + 2 * (size_t)ch.idx;
   const int tilesP = (N + PROPOSE_THREADS - 1) / PROPOSE_THREADS;
   const int tilesS = (N + SCAN_TILE - 1) / SCAN_TILE;
-  const int tilesR = (N + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
+  const int tilesR = (dart_pairs(N) + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;  // two darts per thread
   const long long gridP = (long long)st.count * tilesP;
   if (gridP > 0x7fffffffLL) return e->fail(DCSMC_EINVAL, "step too large for one launch");
   // multilevel leaves: rESS == 1 exactly, so the resample decision is known on the host and the
@@ -611,16 +653,16 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
   const bool leafFused = !javaSums && st.leaf && e->model == DCSMC_MODEL_MULTILEVEL && 1.0 < e->opt.relativeEssThreshold;
 
   if (e->model == DCSMC_MODEL_MARKOV) {
-    ProfScope p(e, DCSMC_K_MARKOV);
-    k_markov_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
+    ProfScope p(e, DCSMC_K_MARKOV, sP);
+    k_markov_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
   } else if (st.leaf) {
     // each warp refills its lanes from a chunk of CH particles (see k_leaf_propose)
     int CH = (N + LEAF_WARPS - 1) / LEAF_WARPS;
     CH = std::min(512, std::max(32, (CH + 31) / 32 * 32));
     const int blocksPerNode = (N + LEAF_WARPS * CH - 1) / (LEAF_WARPS * CH);
     if (leafFused && e->opt.resamplingScheme == DCSMC_MULTINOMIAL) {
-      c.offspring = e->dOffspring;
-      CK(cudaMemsetAsync(e->dOffspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), e->stream));
+      c.offspring = offspring;
+      CK(cudaMemsetAsync(offspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), sP));
     }
     const int mode = !leafFused ? 0 : (e->opt.resamplingScheme == DCSMC_STRATIFIED ? 1 : 2);
     const size_t leafSmem = LEAF_WARPS * leaf_warp_smem_bytes(CH);
@@ -628,12 +670,21 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
       CK(cudaFuncSetAttribute(k_leaf_propose<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leafSmem));
       e->leafSmemSet[RNG] = leafSmem;
     }
-    ProfScope p(e, DCSMC_K_LEAF);
+    ProfScope p(e, DCSMC_K_LEAF, sP);
     k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS,
-                          leafSmem, e->stream>>>(c, blocksPerNode, CH, mode);
+                          leafSmem, sP>>>(c, blocksPerNode, CH, mode);
   } else {
-    ProfScope p(e, DCSMC_K_INTERNAL);
-    k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, e->stream>>>(c, tilesP);
+    {
+      ProfScope p(e, DCSMC_K_INTERNAL, sP);
+      k_internal_prelude<<<(st.count + 3) / 4, 128, 0, sP>>>(c);
+    }
+    ProfScope p(e, DCSMC_K_INTERNAL, sP);
+    k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+  }
+  if (sR != sP) {  // the chain of this chunk starts when its propose kernel is done
+    cudaEvent_t ev = nextEvent(e);
+    CK(cudaEventRecord(ev, sP));
+    CK(cudaStreamWaitEvent(sR, ev, 0));
   }
   const bool smallNode = !st.leaf && !javaSums && N <= SMALLN_MAX;
   if (smallNode) {
@@ -643,60 +694,63 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st) {
       CK(cudaFuncSetAttribute(k_node_small<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       e->smallSmemSet[RNG] = smem;
     }
-    ProfScope p(e, DCSMC_K_SCAN);
-    k_node_small<RNG><<<st.count, SMALLN_THREADS, smem, e->stream>>>(c);
+    ProfScope p(e, DCSMC_K_SCAN, sR);
+    k_node_small<RNG><<<st.count, SMALLN_THREADS, smem, sR>>>(c);
     CK(cudaGetLastError());
     return DCSMC_OK;
   }
   if (st.leaf) {
     // all weights equal: the exact sums are known in closed form, no scan and no CDF
-    ProfScope p(e, DCSMC_K_FINALIZE);
-    k_uniform_stats<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
+    ProfScope p(e, DCSMC_K_FINALIZE, sR);
+    k_uniform_stats<<<(st.count + 127) / 128, 128, 0, sR>>>(c);
   }
   if (javaSums) {
     // parity mode: the reference's sequential sums (also finalises the node statistics)
-    ProfScope p(e, DCSMC_K_SCAN);
-    k_scan_java<<<st.count, 32, 0, e->stream>>>(c);
+    ProfScope p(e, DCSMC_K_SCAN, sR);
+    k_scan_java<<<st.count, 32, 0, sR>>>(c);
   } else {
     if (!st.leaf) {
       const size_t needDesc = (size_t)st.count * tilesS;
-      c.descA = e->dDesc;
-      c.descB = e->dDesc + needDesc;
-      c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + 2 * needDesc);
-      CK(cudaMemsetAsync(e->dDesc, 0, (2 * needDesc + 1) * sizeof(unsigned long long), e->stream));
-      ProfScope p(e, DCSMC_K_SCAN);
-      k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, e->stream>>>(c, tilesS);
+      c.descA = desc;
+      c.descB = desc + needDesc;
+      CK(cudaMemsetAsync(desc, 0, 2 * needDesc * sizeof(unsigned long long), sR));
+      ProfScope p(e, DCSMC_K_SCAN, sR);
+      k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, sR>>>(c, tilesS);
     }
-    ProfScope p(e, DCSMC_K_FINALIZE);
-    k_finalize<<<(st.count + 127) / 128, 128, 0, e->stream>>>(c);
+    ProfScope p(e, DCSMC_K_FINALIZE, sR);
+    k_finalize<<<(st.count + 127) / 128, 128, 0, sR>>>(c);
   }
   if (!st.leaf || javaSums) {
     const int tilesT = (c.invB + 1 + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
-    ProfScope p(e, DCSMC_K_RESAMPLE);
-    k_build_inverse_table<<<(unsigned)(st.count * tilesT), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesT);
+    ProfScope p(e, DCSMC_K_RESAMPLE, sR);
+    k_build_inverse_table<<<(unsigned)(st.count * tilesT), RESAMPLE_THREADS, 0, sR>>>(c, tilesT);
   }
   if (e->opt.resamplingScheme == DCSMC_STRATIFIED) {
     if (!leafFused) {
-      ProfScope p(e, DCSMC_K_RESAMPLE);
-      k_resample_stratified<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+      ProfScope p(e, DCSMC_K_RESAMPLE, sR);
+      k_resample_stratified<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, sR>>>(c, tilesR);
     }
   } else {
     // multinomial: offspring counts by atomics, then scan + expansion (no dart sort)
     const int tilesE = (N + EXPAND_TILE - 1) / EXPAND_TILE;
-    const size_t needDescE = (size_t)st.count * tilesE;
-    c.offspring = e->dOffspring;
-    c.descA = e->dDesc;
-    c.ticket = reinterpret_cast<unsigned int*>(e->dDesc + needDescE);
+    // segments per node: enough blocks to fill the GPU twice, as few look-back hops as possible
+    const int wantBlocks = 2 * e->smCount * (2048 / EXPAND_THREADS);
+    const int segs = std::max(1, std::min(tilesE, (wantBlocks + st.count - 1) / st.count));
+    const int tilesPerSeg = (tilesE + segs - 1) / segs;
+    const int segsPerNode = (tilesE + tilesPerSeg - 1) / tilesPerSeg;
+    c.offspring = offspring;
+    c.descA = desc;
     if (!leafFused) {
-      CK(cudaMemsetAsync(e->dOffspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), e->stream));
-      ProfScope p(e, DCSMC_K_DARTS);
-      k_darts_count<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, e->stream>>>(c, tilesR);
+      CK(cudaMemsetAsync(offspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), sR));
+      ProfScope p(e, DCSMC_K_DARTS, sR);
+      k_darts_count<RNG><<<(unsigned)(st.count * tilesR), RESAMPLE_THREADS, 0, sR>>>(c, tilesR);
     }
     // the look-back descriptors of the scan are dead by now (stream order): reuse them
-    CK(cudaMemsetAsync(e->dDesc, 0, (needDescE + 1) * sizeof(unsigned long long), e->stream));
+    if (segsPerNode > 1)
+      CK(cudaMemsetAsync(desc, 0, (size_t)st.count * segsPerNode * sizeof(unsigned long long), sR));
     {
-      ProfScope p(e, DCSMC_K_RESAMPLE);
-      k_expand<<<(unsigned)(st.count * tilesE), EXPAND_THREADS, 0, e->stream>>>(c, tilesE);
+      ProfScope p(e, DCSMC_K_RESAMPLE, sR);
+      k_expand<<<(unsigned)(st.count * segsPerNode), EXPAND_THREADS, 0, sR>>>(c, segsPerNode, tilesPerSeg);
     }
   }
   CK(cudaGetLastError());
@@ -763,7 +817,6 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     maxStep = std::max<size_t>(maxStep, s.count);
     if (!s.leaf || e->opt.sumMode == DCSMC_SUM_JAVA) maxInternalStep = std::max<size_t>(maxInternalStep, s.count);
   }
-  const size_t tilesS = (N + SCAN_TILE - 1) / SCAN_TILE;
   auto grow = [&](void** p, size_t& cap, size_t need, size_t elem) -> cudaError_t {
     if (need <= cap) return cudaSuccess;
     if (*p) cudaFree(*p);
@@ -773,12 +826,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     return r;
   };
   CK(grow((void**)&e->dCdf, e->cdfCap, std::max<size_t>(1, maxInternalStep * (size_t)e->Npad), sizeof(double)));
-  {
-    const size_t tilesE = (N + EXPAND_TILE - 1) / EXPAND_TILE;
-    size_t needDesc = 2 * maxInternalStep * tilesS + 1;
-    if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL) needDesc = std::max(needDesc, maxStep * tilesE + 1);
-    CK(grow((void**)&e->dDesc, e->descCap, needDesc, sizeof(unsigned long long)));
-  }
+  CK(grow((void**)&e->dDesc, e->descCap, maxStep * descWordsPerNode(N) + 2 * MAX_CHUNKS + 2, sizeof(unsigned long long)));
   e->invB = 1;
   while ((size_t)e->invB * 8 < (size_t)N) e->invB <<= 1;
   CK(grow((void**)&e->dInvTable, e->invTableCap, std::max<size_t>(1, maxInternalStep * ((size_t)e->invB + 1)), sizeof(int32_t)));
@@ -838,13 +886,35 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   e->info.d2hBytes = (int64_t)(sizeof(NodeStats) * e->nNodes);
   e->pendingH2D = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
+  // level batches, each cut into chunks whose chains overlap the next chunk's propose kernel
+  const bool overlap = !e->profile && e->overlapChunks > 1 && e->streamR != nullptr;
+  e->evNext = 0;
+  cudaEvent_t chainDone = nullptr;  // last chain work of the previous level batch
   for (auto& s : plan.steps) {
-    switch (e->opt.rngMode) {
-      case DCSMC_RNG_PHILOX: rc = launchStep<RNG_PHILOX>(e, c, s); break;
-      case DCSMC_RNG_INJECTED: rc = launchStep<RNG_INJECTED>(e, c, s); break;
-      default: rc = launchStep<RNG_JAVA>(e, c, s); break;
+    int nCh = 1;
+    if (overlap) nCh = std::max(1, std::min({e->overlapChunks, MAX_CHUNKS, s.count / 8}));
+    if (chainDone) {  // children must be complete (and the scratch free) before this level starts
+      CK(cudaStreamWaitEvent(e->stream, chainDone, 0));
+      chainDone = nullptr;
     }
-    if (rc) return rc;
+    for (int k = 0; k < nCh; ++k) {
+      const int lo = (int)((long long)s.count * k / nCh), hi = (int)((long long)s.count * (k + 1) / nCh);
+      Step sub;
+      sub.offset = s.offset + lo;
+      sub.count = hi - lo;
+      sub.leaf = s.leaf;
+      const ChunkCtx ch{e->stream, nCh > 1 ? e->streamR : e->stream, lo, k};
+      switch (e->opt.rngMode) {
+        case DCSMC_RNG_PHILOX: rc = launchStep<RNG_PHILOX>(e, c, sub, ch); break;
+        case DCSMC_RNG_INJECTED: rc = launchStep<RNG_INJECTED>(e, c, sub, ch); break;
+        default: rc = launchStep<RNG_JAVA>(e, c, sub, ch); break;
+      }
+      if (rc) return rc;
+    }
+    if (nCh > 1) {
+      chainDone = nextEvent(e);
+      CK(cudaEventRecord(chainDone, e->streamR));
+    }
     e->info.levelBatches++;
     e->info.nodesProcessed += s.count;
     for (int k = 0; k < s.count; ++k) {
@@ -854,6 +924,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
           (int64_t)N * (40 * C + 184 + (e->opt.resamplingScheme == DCSMC_MULTINOMIAL ? 16 : 0));
     }
   }
+  if (chainDone) CK(cudaStreamWaitEvent(e->stream, chainDone, 0));
   CK(cudaEventRecord(e->ev1, e->stream));
   // fetch the statistics of the nodes this plan computed
   const bool fewNodes = plan.stepNodes.size() * 16 < (size_t)e->nNodes;
@@ -1005,7 +1076,14 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   }
   dcsmc_engine* e = new dcsmc_engine();
   e->opt = *opt;
-  if (cudaSetDevice(opt->device) != cudaSuccess || cudaStreamCreate(&e->stream) != cudaSuccess ||
+  int prLow = 0, prHigh = 0;
+  if (cudaSetDevice(opt->device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
+  cudaDeviceGetAttribute(&e->smCount, cudaDevAttrMultiProcessorCount, opt->device);
+  if (e->smCount <= 0) e->smCount = 148;
+  if (const char* v = getenv("DCSMC_OVERLAP_CHUNKS")) e->overlapChunks = std::max(1, atoi(v));
+  if (cudaSetDevice(opt->device) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prLow) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&e->streamR, cudaStreamNonBlocking, prHigh) != cudaSuccess ||
       cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
     g_createError = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
     delete e;
@@ -1024,6 +1102,8 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   for (Slot& sl : e->slot)
     if (sl.external) cudaFree(sl.external);
   for (char* p : e->importFree) cudaFree(p);
+  if (e->hStage) cudaFreeHost(e->hStage);
+  if (e->dStage) cudaFree(e->dStage);
   void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dStepNodesTmp, e->dInj, e->dJavaState,
                   e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable};
   for (void* p : ptrs)
@@ -1031,6 +1111,8 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->streamR) cudaStreamDestroy(e->streamR);
+  for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
   delete e;
   return DCSMC_OK;
 }
@@ -1199,24 +1281,33 @@ int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* sta
     return e->fail(DCSMC_ESTATE, "population of node %d is not resident (consumed by its parent, or not computed)", node);
   CK(cudaSetDevice(e->opt.device));
   const int N = e->opt.nParticles;
-  double* dS = nullptr;
-  int32_t* dI = nullptr;
-  double* dW = nullptr;
-  if (state) CK(cudaMalloc((void**)&dS, sizeof(double) * 6 * N));
-  if (istate) CK(cudaMalloc((void**)&dI, sizeof(int32_t) * N));
-  if (weights) CK(cudaMalloc((void**)&dW, sizeof(double) * N));
+  // device staging + pinned host staging, both kept across calls: the copy runs at PCIe speed into
+  // pinned memory and the caller's (pageable) arrays are filled by a plain memcpy
+  const size_t bS = state ? sizeof(double) * 6 * (size_t)N : 0, bI = istate ? sizeof(int32_t) * (size_t)N : 0,
+               bW = weights ? sizeof(double) * (size_t)N : 0;
+  const size_t oI = alignUp(bS, 256), oW = oI + alignUp(bI, 256), total = oW + alignUp(bW, 256);
+  if (total > e->stageCap) {
+    if (e->dStage) cudaFree(e->dStage);
+    if (e->hStage) cudaFreeHost(e->hStage);
+    e->dStage = e->hStage = nullptr;
+    e->stageCap = 0;
+    CK(cudaMalloc((void**)&e->dStage, total));
+    CK(cudaMallocHost((void**)&e->hStage, total));
+    e->stageCap = total;
+  }
+  double* dS = state ? reinterpret_cast<double*>(e->dStage) : nullptr;
+  int32_t* dI = istate ? reinterpret_cast<int32_t*>(e->dStage + oI) : nullptr;
+  double* dW = weights ? reinterpret_cast<double*>(e->dStage + oW) : nullptr;
   RunCtx c;
   makeCtx(e, c);
   e->info.kernelLaunches++;
   k_materialise<<<(N + 255) / 256, 256, 0, e->stream>>>(c, node, dS, dI, dW, (size_t)N);
   CK(cudaGetLastError());
-  if (state) CK(cudaMemcpyAsync(state, dS, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, e->stream));
-  if (istate) CK(cudaMemcpyAsync(istate, dI, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, e->stream));
-  if (weights) CK(cudaMemcpyAsync(weights, dW, sizeof(double) * N, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->hStage, e->dStage, total, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  if (dS) cudaFree(dS);
-  if (dI) cudaFree(dI);
-  if (dW) cudaFree(dW);
+  if (state) memcpy(state, e->hStage, bS);
+  if (istate) memcpy(istate, e->hStage + oI, bI);
+  if (weights) memcpy(weights, e->hStage + oW, bW);
   return DCSMC_OK;
 }
 
