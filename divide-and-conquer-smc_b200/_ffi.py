@@ -75,7 +75,10 @@ SYMBOLS = [
     "dcsmc_debug_copy_node", "dcsmc_population_packed_bytes", "dcsmc_population_pack",
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
     "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval", "dcsmc_reset_populations",
+    "dcsmc_timer_begin", "dcsmc_timer_end",
+    "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
 ]
+IPC_HANDLE_BYTES, EXPORT_DESC_BYTES = 64, 128
 
 _lib = None
 
@@ -118,6 +121,12 @@ def lib():
     L.dcsmc_population_release.argtypes = [vp, i32]
     L.dcsmc_reset_populations.argtypes = [vp]
     L.dcsmc_last_run_info.argtypes = [vp, P(RunInfo)]
+    L.dcsmc_peer_pool_handle.argtypes = [vp, vp, P(i64)]
+    L.dcsmc_peer_open.argtypes = [vp, i32, vp, i64]
+    L.dcsmc_population_export.argtypes = [vp, P(i32), i32, vp]
+    L.dcsmc_population_import_peer.argtypes = [vp, P(i32), P(i32), i32, vp]
+    L.dcsmc_timer_begin.argtypes = [vp]
+    L.dcsmc_timer_end.argtypes = [vp, P(dbl)]
     L.dcsmc_profile_enable.argtypes = [vp, i32]
     L.dcsmc_profile_get.argtypes = [vp, i32, P(dbl), P(i64)]
     L.dcsmc_debug_eval.argtypes = [vp, i32, P(dbl), P(dbl), i64]

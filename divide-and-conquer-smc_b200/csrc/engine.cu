@@ -38,6 +38,7 @@ struct Slot {
   size_t offset = 0;
   size_t bytes = 0;
   char* external = nullptr;  // unpacked populations live in their own allocation, not in the pool
+  bool peer = false;         // `external` points into a peer engine's pool (not owned, never recycled)
 };
 
 struct Plan {
@@ -55,6 +56,7 @@ struct CachedPlan {
   std::vector<Slot> slot;
   std::vector<char> resident, imported;
   std::vector<char> inPlan;  // per node: computed by this plan
+  std::vector<int> finalResident;  // nodes still resident when the plan has run (its roots, unless retained)
 };
 
 }  // namespace
@@ -113,7 +115,17 @@ struct dcsmc_engine {
   bool undoOn = false;
   std::vector<NodeDev> hNodes;   // host mirror
   std::vector<dcsmc_node_stats_t> hStats;
-  std::vector<NodeStats> hStatsRaw;  // host staging of the device statistics table
+  std::vector<NodeStatsOut> hOut;   // per node: last fetched record (incl. m, S for exports)
+  std::vector<int> statNodes;       // nodes whose hStats entry was written since the last reset
+  std::vector<int> externalNodes;   // nodes that got an external slot since the last reset
+  struct PeerMap { char* base = nullptr; int64_t generation = -1; };
+  std::map<int, PeerMap> peers;     // peer engines' pools mapped through CUDA IPC
+  int64_t poolGeneration = 0;       // bumped whenever the pool is (re)allocated
+  char *dImp = nullptr, *hImp = nullptr;  // dcsmc_population_import_peer staging
+  size_t impCap = 0;
+  NodeStatsOut *dExport = nullptr, *hExport = nullptr;  // statistics of the last plan (device / pinned host)
+  size_t exportCap = 0;
+  cudaEvent_t evT0 = nullptr, evT1 = nullptr;           // dcsmc_timer_begin / dcsmc_timer_end
   int Npad = 0;
 
   // scratch
@@ -251,9 +263,10 @@ void poolFree(dcsmc_engine* e, int n) {
   if (!e->resident[n]) return;
   if (e->undoOn) e->undo.push_back({n, e->slot[n], e->resident[n], e->imported[n]});
   e->resident[n] = 0;
-  if (e->slot[n].external) {  // unpacked population: recycle its buffer
-    e->importFree.push_back(e->slot[n].external);
+  if (e->slot[n].external) {  // unpacked population: recycle its buffer (peer memory is not ours)
+    if (!e->slot[n].peer) e->importFree.push_back(e->slot[n].external);
     e->slot[n].external = nullptr;
+    e->slot[n].peer = false;
     e->imported[n] = 0;
     return;
   }
@@ -286,7 +299,8 @@ void fillNodeDev(dcsmc_engine* e, int n) {
   d.nChildren = nChildrenOf(e, n);
   d.kind = nodeKind(e, n);
   d.pad = 0;
-  if (!e->imported.empty() && e->imported[n]) d.kind = KIND_INTERNAL;  // unpacked: 6 columns + logw
+  // unpacked (imported == 1): 6 columns + logw; peer-mapped (imported == 2): the owner's native layout
+  if (!e->imported.empty() && e->imported[n] == 1) d.kind = KIND_INTERNAL;
   const bool internal = d.kind == KIND_INTERNAL;
   if (e->model == DCSMC_MODEL_MARKOV) {
     d.state = nullptr;
@@ -385,8 +399,11 @@ int uploadTables(dcsmc_engine* e) {
   CK(cudaStreamSynchronize(e->stream));
   e->hNodes.assign(nN, NodeDev{});
   e->hStats.assign(nN, dcsmc_node_stats_t{});
+  e->hOut.assign(nN, NodeStatsOut{});
+  e->statNodes.clear();
+  e->externalNodes.clear();
   for (Slot& sl : e->slot)  // buffers of unpacked populations (their size depends on the model)
-    if (sl.external) cudaFree(sl.external);
+    if (sl.external && !sl.peer) cudaFree(sl.external);
   for (char* p : e->importFree) cudaFree(p);
   e->importFree.clear();
   e->slot.assign(nN, Slot{});
@@ -438,6 +455,7 @@ int ensurePool(dcsmc_engine* e) {
   e->poolBytes = std::min(budget, all);
   e->poolIsBudget = e->poolBytes < all;
   CK(cudaMalloc((void**)&e->pool, e->poolBytes));
+  e->poolGeneration++;  // peers holding a mapping of the old pool must re-open (dcsmc_peer_pool_handle)
   return DCSMC_OK;
 }
 
@@ -506,7 +524,7 @@ void restorePool(dcsmc_engine* e, const PoolState& s) {
   e->poolTop = s.poolTop;
   while (e->undo.size() > s.undoMark) {
     const dcsmc_engine::Undo& u = e->undo.back();
-    if (u.slot.external) {  // the trial recycled this unpacked population's buffer: take it back
+    if (u.slot.external && !u.slot.peer) {  // the trial recycled this unpacked population's buffer: take it back
       auto it = std::find(e->importFree.begin(), e->importFree.end(), u.slot.external);
       if (it != e->importFree.end()) e->importFree.erase(it);
     }
@@ -808,9 +826,27 @@ int validateForRun(dcsmc_engine* e) {
 }
 
 // run a plan: upload step lists, execute, fetch stats
+// an error left behind by an unchecked runtime call must not be blamed on the next checked one
+#define CKPOINT(label)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return e->fail(DCSMC_ECUDA, "pending CUDA error at %s: %s", label, cudaGetErrorString(_e)); \
+  } while (0)
+
+// the device holds the step lists and node descriptors of this cached plan, untouched since
+bool descriptorsValid(const dcsmc_engine* e, const CachedPlan* cached) {
+  if (cached == nullptr || e->devicePlan != cached) return false;
+  // other plans / unpack may have rewritten descriptors since; they only matter if they hit this plan
+  for (int n : e->descDirty)
+    if (cached->inPlan[n]) return false;
+  return true;
+}
+
 int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr) {
   int rc;
   const int N = e->opt.nParticles;
+  CKPOINT("executePlan entry");
   // scratch sizing: CDF + look-back descriptors for internal steps, darts for multinomial
   size_t maxStep = 0, maxInternalStep = 0;
   for (auto& s : plan.steps) {
@@ -827,20 +863,13 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   };
   CK(grow((void**)&e->dCdf, e->cdfCap, std::max<size_t>(1, maxInternalStep * (size_t)e->Npad), sizeof(double)));
   CK(grow((void**)&e->dDesc, e->descCap, maxStep * descWordsPerNode(N) + 2 * MAX_CHUNKS + 2, sizeof(unsigned long long)));
+  CKPOINT("scratch growth");
   e->invB = 1;
   while ((size_t)e->invB * 8 < (size_t)N) e->invB <<= 1;
   CK(grow((void**)&e->dInvTable, e->invTableCap, std::max<size_t>(1, maxInternalStep * ((size_t)e->invB + 1)), sizeof(int32_t)));
   if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL)
     CK(grow((void**)&e->dOffspring, e->offspringCap, maxStep * (size_t)e->Npad, sizeof(int32_t)));
-  bool descriptorsOnDevice = cached != nullptr && e->devicePlan == cached;
-  if (descriptorsOnDevice) {
-    // other plans / unpack may have rewritten descriptors since; they only matter if they hit this plan
-    for (int n : e->descDirty)
-      if (cached->inPlan[n]) {
-        descriptorsOnDevice = false;
-        break;
-      }
-  }
+  bool descriptorsOnDevice = descriptorsValid(e, cached);
   if (cached != nullptr) e->descDirty.clear();
   {
     int32_t*& buf = cached ? e->dStepNodes : e->dStepNodesTmp;
@@ -872,6 +901,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     }
     if (cached != nullptr) e->devicePlan = cached;
   }
+  CKPOINT("descriptor upload");
   // accumulators of the nodes about to be recomputed start from zero
   if (!plan.stepNodes.empty()) {
     const int n = (int)plan.stepNodes.size();
@@ -883,7 +913,6 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   e->info = dcsmc_run_info{};
   e->info.poolBytes = (int64_t)e->poolBytes;
   e->info.h2dBytes = e->pendingH2D + (descriptorsOnDevice ? 0 : (int64_t)(plan.stepNodes.size() * sizeof(int32_t) + sizeof(NodeDev) * e->nNodes));
-  e->info.d2hBytes = (int64_t)(sizeof(NodeStats) * e->nNodes);
   e->pendingH2D = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
   // level batches, each cut into chunks whose chains overlap the next chunk's propose kernel
@@ -926,31 +955,41 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   }
   if (chainDone) CK(cudaStreamWaitEvent(e->stream, chainDone, 0));
   CK(cudaEventRecord(e->ev1, e->stream));
-  // fetch the statistics of the nodes this plan computed
-  const bool fewNodes = plan.stepNodes.size() * 16 < (size_t)e->nNodes;
-  if ((int)e->hStatsRaw.size() != e->nNodes) e->hStatsRaw.assign(e->nNodes, NodeStats{});
-  std::vector<NodeStats>& hs = e->hStatsRaw;
-  if (fewNodes) {
-    for (int n : plan.stepNodes)
-      CK(cudaMemcpyAsync(&hs[n], e->dStats + n, sizeof(NodeStats), cudaMemcpyDeviceToHost, e->stream));
-    e->info.d2hBytes = (int64_t)(sizeof(NodeStats) * plan.stepNodes.size());
-  } else {
-    CK(cudaMemcpyAsync(hs.data(), e->dStats, sizeof(NodeStats) * e->nNodes, cudaMemcpyDeviceToHost, e->stream));
+  CKPOINT("level batches");
+  // fetch the statistics of the nodes this plan computed: compact records, pinned staging
+  const size_t nPlan = plan.stepNodes.size();
+  if (nPlan > e->exportCap) {
+    if (e->dExport) cudaFree(e->dExport);
+    if (e->hExport) cudaFreeHost(e->hExport);
+    e->dExport = e->hExport = nullptr;
+    e->exportCap = 0;
+    CK(cudaMalloc((void**)&e->dExport, nPlan * sizeof(NodeStatsOut)));
+    CK(cudaMallocHost((void**)&e->hExport, nPlan * sizeof(NodeStatsOut)));
+    e->exportCap = nPlan;
   }
+  if (nPlan > 0) {
+    k_export_stats<<<(unsigned)((nPlan + 255) / 256), 256, 0, e->stream>>>(e->dStats, e->curStepNodes, (int)nPlan, e->dExport);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->hExport, e->dExport, nPlan * sizeof(NodeStatsOut), cudaMemcpyDeviceToHost, e->stream));
+  }
+  e->info.d2hBytes = (int64_t)(nPlan * sizeof(NodeStatsOut));
   CK(cudaStreamSynchronize(e->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->info.deviceMs = ms;
   e->info.particleUpdates = e->info.nodesProcessed * (int64_t)N;
-  for (int n : plan.stepNodes) {
-    dcsmc_node_stats_t& o = e->hStats[n];
-    o.ess = hs[n].ess;
-    o.relEss = hs[n].relEss;
-    o.logNormEstimate = hs[n].logZ;
-    o.logScaling = hs[n].logScaling;
-    o.resampled = hs[n].resampled == RES_WEIGHTED ? 0 : 1;
-    o.done = hs[n].done;
+  for (size_t k = 0; k < nPlan; ++k) {
+    const NodeStatsOut& h = e->hExport[k];
+    dcsmc_node_stats_t& o = e->hStats[plan.stepNodes[k]];
+    o.ess = h.ess;
+    o.relEss = h.relEss;
+    o.logNormEstimate = h.logZ;
+    o.logScaling = h.logScaling;
+    o.resampled = h.resampled == RES_WEIGHTED ? 0 : 1;
+    o.done = h.done;
+    e->hOut[plan.stepNodes[k]] = h;
   }
+  e->statNodes.insert(e->statNodes.end(), plan.stepNodes.begin(), plan.stepNodes.end());
   if (e->profile) {
     for (auto& pe : e->profEvents) {
       float t = 0;
@@ -991,9 +1030,18 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
       if (cp.roots == roots) {
         e->freeBySize = cp.freeBySize;
         e->poolTop = cp.poolTop;
-        e->slot = cp.slot;
-        e->resident = cp.resident;
-        e->imported = cp.imported;
+        if (descriptorsValid(e, &cp) && cp.finalResident.size() * 8 < (size_t)e->nNodes) {
+          // the device already holds this plan's descriptors and the pool is empty: only the nodes that
+          // stay resident need their host-side slot back (O(roots), not O(nNodes))
+          for (int n : cp.finalResident) {
+            e->slot[n] = cp.slot[n];
+            e->resident[n] = 1;
+          }
+        } else {
+          e->slot = cp.slot;
+          e->resident = cp.resident;
+          e->imported = cp.imported;
+        }
         return executePlan(e, cp.plan, &cp);
       }
   }
@@ -1010,7 +1058,10 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
     cp.resident = e->resident;
     cp.imported = e->imported;
     cp.inPlan.assign(e->nNodes, 0);
-    for (int n : plan.stepNodes) cp.inPlan[n] = 1;
+    for (int n : plan.stepNodes) {
+      cp.inPlan[n] = 1;
+      if (e->resident[n]) cp.finalResident.push_back(n);
+    }
     e->planCache.push_back(std::move(cp));
     return executePlan(e, e->planCache.back().plan, &e->planCache.back());
   }
@@ -1095,24 +1146,49 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
 
 int32_t dcsmc_destroy(dcsmc_engine* e) {
   if (!e) return DCSMC_OK;
+  const bool dbg = getenv("DCSMC_DEBUG") != nullptr;
+  auto chk = [&](const char* what) {  // never leave an error behind for the next engine of this thread
+    const cudaError_t r = cudaGetLastError();
+    if (r != cudaSuccess && dbg) fprintf(stderr, "dcsmc_destroy: %s: %s\n", what, cudaGetErrorString(r));
+  };
   cudaSetDevice(e->opt.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  chk("entry");
   for (double* p : e->injDev)
     if (p) cudaFree(p);
+  chk("injected uniforms");
   for (Slot& sl : e->slot)
-    if (sl.external) cudaFree(sl.external);
+    if (sl.external && !sl.peer) cudaFree(sl.external);
   for (char* p : e->importFree) cudaFree(p);
+  chk("imported populations");
+  for (auto& kv : e->peers)
+    if (kv.second.base) cudaIpcCloseMemHandle(kv.second.base);
+  chk("peer mappings");
+  if (e->hImp) cudaFreeHost(e->hImp);
+  if (e->dImp) cudaFree(e->dImp);
+  chk("import staging");
+  if (e->hExport) cudaFreeHost(e->hExport);
+  chk("export staging (host)");
+  if (e->dExport) cudaFree(e->dExport);
+  chk("export staging (device)");
+  if (e->evT0) cudaEventDestroy(e->evT0);
+  if (e->evT1) cudaEventDestroy(e->evT1);
+  chk("timer events");
   if (e->hStage) cudaFreeHost(e->hStage);
+  chk("population staging (host)");
   if (e->dStage) cudaFree(e->dStage);
+  chk("population staging (device)");
   void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dStepNodesTmp, e->dInj, e->dJavaState,
                   e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  chk("tables");
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->streamR) cudaStreamDestroy(e->streamR);
   for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
+  chk("streams and events");
   delete e;
   return DCSMC_OK;
 }
@@ -1423,6 +1499,8 @@ int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* devic
     CK(cudaMalloc((void**)&buf, importBytes(e)));
   }
   e->slot[node] = Slot{0, 0, buf};
+  e->externalNodes.push_back(node);
+  e->statNodes.push_back(node);
   e->resident[node] = 1;
   e->imported[node] = 1;
   fillNodeDev(e, node);
@@ -1445,16 +1523,174 @@ int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* devic
   return DCSMC_OK;
 }
 
+// ---- zero-copy sharing over NVLink peer memory ---------------------------------------------------
+// Wire format of one exported population (DCSMC_EXPORT_DESC_BYTES host bytes).
+struct ExportDesc {
+  int32_t magic, N;
+  int64_t offset;       // of the population inside the owner's pool
+  int64_t generation;   // of that pool
+  double m, S, ess, relEss, logScaling, logZ;
+  int32_t resampled, done;
+  char pad[DCSMC_EXPORT_DESC_BYTES - 80];
+};
+static_assert(sizeof(ExportDesc) == DCSMC_EXPORT_DESC_BYTES, "export descriptor size");
+
+int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generation) {
+  if (!e || !handle || !generation) return DCSMC_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == DCSMC_IPC_HANDLE_BYTES, "IPC handle size");
+  int rc;
+  if ((rc = prepare(e))) return rc;  // allocates the pool
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->pool));
+  memcpy(handle, &h, sizeof h);
+  *generation = e->poolGeneration;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64_t generation) {
+  if (!e || !handle || peer < 0) return DCSMC_EINVAL;
+  CK(cudaSetDevice(e->opt.device));
+  dcsmc_engine::PeerMap& pm = e->peers[peer];
+  if (pm.base && pm.generation == generation) return DCSMC_OK;
+  if (pm.base) {
+    cudaIpcCloseMemHandle(pm.base);
+    pm.base = nullptr;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  pm.base = static_cast<char*>(p);
+  pm.generation = generation;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* descs) {
+  if (!e || n < 0 || (n > 0 && (!nodes || !descs))) return DCSMC_EINVAL;
+  ExportDesc* out = static_cast<ExportDesc*>(descs);
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+    if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+      return e->fail(DCSMC_ESTATE, "population of node %d is not resident", node);
+    if (e->slot[node].external)
+      return e->fail(DCSMC_ESTATE, "node %d is itself an imported population; only pool residents can be exported", node);
+    const NodeStatsOut& h = e->hOut[node];
+    ExportDesc d;
+    memset(&d, 0, sizeof d);
+    d.magic = PACK_MAGIC;
+    d.N = e->opt.nParticles;
+    d.offset = (int64_t)e->slot[node].offset;
+    d.generation = e->poolGeneration;
+    d.m = h.m;
+    d.S = h.S;
+    d.ess = h.ess;
+    d.relEss = h.relEss;
+    d.logScaling = h.logScaling;
+    d.logZ = h.logZ;
+    d.resampled = h.resampled;
+    d.done = 1;
+    out[k] = d;
+  }
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, const int32_t* peerIds, int32_t n,
+                                     const void* descs) {
+  if (!e || n < 0 || (n > 0 && (!nodes || !peerIds || !descs))) return DCSMC_EINVAL;
+  if (n == 0) return DCSMC_OK;
+  int rc;
+  if ((rc = prepare(e))) return rc;
+  const ExportDesc* in = static_cast<const ExportDesc*>(descs);
+  const size_t oNd = alignUp(sizeof(int32_t) * n, 256), oSt = oNd + alignUp(sizeof(NodeDev) * n, 256),
+               total = oSt + alignUp(sizeof(NodeStats) * n, 256);
+  if (total > e->impCap) {
+    if (e->dImp) cudaFree(e->dImp);
+    if (e->hImp) cudaFreeHost(e->hImp);
+    e->dImp = e->hImp = nullptr;
+    e->impCap = 0;
+    CK(cudaMalloc((void**)&e->dImp, total));
+    CK(cudaMallocHost((void**)&e->hImp, total));
+    e->impCap = total;
+  }
+  int32_t* hIds = reinterpret_cast<int32_t*>(e->hImp);
+  NodeDev* hNd = reinterpret_cast<NodeDev*>(e->hImp + oNd);
+  NodeStats* hSt = reinterpret_cast<NodeStats*>(e->hImp + oSt);
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    const ExportDesc& d = in[k];
+    if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+    if (d.magic != PACK_MAGIC || d.N != e->opt.nParticles)
+      return e->fail(DCSMC_EINVAL, "exported population of node %d does not match this engine (magic/N)", node);
+    auto it = e->peers.find(peerIds[k]);
+    if (it == e->peers.end() || !it->second.base || it->second.generation != d.generation)
+      return e->fail(DCSMC_ESTATE, "pool of peer %d (generation %lld) is not mapped: call dcsmc_peer_open", peerIds[k],
+                     (long long)d.generation);
+    poolFree(e, node);
+    Slot sl;
+    sl.external = it->second.base + d.offset;
+    sl.peer = true;
+    e->slot[node] = sl;
+    e->externalNodes.push_back(node);
+    e->statNodes.push_back(node);
+    e->resident[node] = 1;
+    e->imported[node] = 2;
+    fillNodeDev(e, node);
+    e->descDirty.push_back(node);
+    hIds[k] = node;
+    hNd[k] = e->hNodes[node];
+    NodeStats z;
+    memset(&z, 0, sizeof z);
+    z.maxKey = ordered_key(d.m);
+    z.m = d.m;
+    z.S = d.S;
+    z.ess = d.ess;
+    z.relEss = d.relEss;
+    z.logScaling = d.logScaling;
+    z.logZ = d.logZ;
+    z.resampled = d.resampled;
+    z.done = 1;
+    hSt[k] = z;
+    dcsmc_node_stats_t& o = e->hStats[node];
+    o.ess = d.ess;
+    o.relEss = d.relEss;
+    o.logNormEstimate = d.logZ;
+    o.logScaling = d.logScaling;
+    o.resampled = d.resampled == RES_WEIGHTED ? 0 : 1;
+    o.done = 1;
+    NodeStatsOut& ho = e->hOut[node];
+    ho.ess = d.ess; ho.relEss = d.relEss; ho.logZ = d.logZ; ho.logScaling = d.logScaling;
+    ho.m = d.m; ho.S = d.S; ho.resampled = d.resampled; ho.done = 1;
+  }
+  CK(cudaMemcpyAsync(e->dImp, e->hImp, total, cudaMemcpyHostToDevice, e->stream));
+  e->info.kernelLaunches++;
+  k_scatter_import<<<(n + 127) / 128, 128, 0, e->stream>>>(e->dNodes, e->dStats, reinterpret_cast<int32_t*>(e->dImp),
+                                                          reinterpret_cast<NodeDev*>(e->dImp + oNd),
+                                                          reinterpret_cast<NodeStats*>(e->dImp + oSt), n);
+  CK(cudaGetLastError());
+  return DCSMC_OK;  // stream order: the next run on this engine sees the imported descriptors
+}
+
 int32_t dcsmc_reset_populations(dcsmc_engine* e) {
   if (!e) return DCSMC_EINVAL;
-  for (size_t n = 0; n < e->slot.size(); ++n)
-    if (e->slot[n].external) {
-      e->importFree.push_back(e->slot[n].external);
+  // O(nodes touched since the last reset), not O(nNodes): a rank of a sharded run only ever touches
+  // its own part of a large tree
+  for (int n : e->externalNodes)
+    if (n < (int)e->slot.size() && e->slot[n].external) {
+      if (!e->slot[n].peer) e->importFree.push_back(e->slot[n].external);
       e->slot[n].external = nullptr;
+      e->slot[n].peer = false;
     }
+  e->externalNodes.clear();
+  if (e->statNodes.size() * 4 > e->hStats.size()) {
+    std::fill(e->hStats.begin(), e->hStats.end(), dcsmc_node_stats_t{});
+  } else {
+    for (int n : e->statNodes)
+      if (n < (int)e->hStats.size()) e->hStats[n] = dcsmc_node_stats_t{};
+  }
+  e->statNodes.clear();
   std::fill(e->resident.begin(), e->resident.end(), 0);
   std::fill(e->imported.begin(), e->imported.end(), 0);
-  for (auto& s : e->hStats) s = dcsmc_node_stats_t{};
   e->freeBySize.clear();
   e->poolTop = 0;
   return DCSMC_OK;
@@ -1470,6 +1706,29 @@ int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node) {
 int32_t dcsmc_last_run_info(const dcsmc_engine* e, dcsmc_run_info* out) {
   if (!e || !out) return DCSMC_EINVAL;
   *out = e->info;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_timer_begin(dcsmc_engine* e) {
+  if (!e) return DCSMC_EINVAL;
+  CK(cudaSetDevice(e->opt.device));
+  if (!e->evT0) {
+    CK(cudaEventCreate(&e->evT0));
+    CK(cudaEventCreate(&e->evT1));
+  }
+  CK(cudaEventRecord(e->evT0, e->stream));
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_timer_end(dcsmc_engine* e, double* ms) {
+  if (!e || !ms) return DCSMC_EINVAL;
+  if (!e->evT0) return e->fail(DCSMC_ESTATE, "dcsmc_timer_end without dcsmc_timer_begin");
+  CK(cudaSetDevice(e->opt.device));
+  CK(cudaEventRecord(e->evT1, e->stream));
+  CK(cudaEventSynchronize(e->evT1));
+  float t = 0;
+  CK(cudaEventElapsedTime(&t, e->evT0, e->evT1));
+  *ms = t;
   return DCSMC_OK;
 }
 

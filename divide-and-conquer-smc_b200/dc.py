@@ -361,10 +361,11 @@ class DistributedDC:
                     stack.extend(int(c) for c in self.csr.children[self.csr.childOffsets[n]:self.csr.childOffsets[n + 1]])
             self.plan, self._planWorld, self._nodeOwner = plan, world, own
             self._xferBufs = {}
-            for lvl in plan.top_levels:
-                for child, src, dst in lvl.transfers:
-                    if rank in (src, dst):
-                        self._xferBufs[child] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            if self._transport(dist, dev) != "p2p":
+                for lvl in plan.top_levels:
+                    for child, src, dst in lvl.transfers:
+                        if rank in (src, dst):
+                            self._xferBufs[child] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         plan, own = self.plan, self._nodeOwner
         e.reset_populations()
         launches = updates = algbytes = nvbytes = 0
@@ -382,37 +383,158 @@ class DistributedDC:
         if mine:
             e.run_subtrees(mine)
             account()
-        for lvl in plan.top_levels:
-            ops, recvs, sends = [], [], []
-            for child, src, dst in lvl.transfers:
-                if rank == src:
-                    buf = self._xferBufs[child]
-                    e.pack(child, buf.data_ptr())
+        if self._transport(dist, dev) == "p2p":
+            nvbytes = self._top_levels_p2p(dist, dev, plan, rank, world, account)
+            launches += sum(1 for lvl in plan.top_levels if any(d == rank for _, _, d in lvl.transfers))
+        else:
+            for lvl in plan.top_levels:
+                ops, recvs, sends = [], [], []
+                for child, src, dst in lvl.transfers:
+                    if rank == src:
+                        buf = self._xferBufs[child]
+                        e.pack(child, buf.data_ptr())
+                        launches += 1
+                        sends.append((child, buf))
+                        ops.append(dist.P2POp(dist.isend, buf, dst))
+                    elif rank == dst:
+                        buf = self._xferBufs[child]
+                        recvs.append((child, buf))
+                        ops.append(dist.P2POp(dist.irecv, buf, src))
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+                    if dev.type == "cuda":
+                        torch.cuda.current_stream(dev).synchronize()
+                for child, buf in sends:
+                    e.release(child)
+                    nvbytes += nbytes
+                for child, buf in recvs:
+                    e.unpack(child, buf.data_ptr())
                     launches += 1
-                    sends.append((child, buf))
-                    ops.append(dist.P2POp(dist.isend, buf, dst))
-                elif rank == dst:
-                    buf = self._xferBufs[child]
-                    recvs.append((child, buf))
-                    ops.append(dist.P2POp(dist.irecv, buf, src))
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-                if dev.type == "cuda":
-                    torch.cuda.current_stream(dev).synchronize()
-            for child, buf in sends:
-                e.release(child)
-                nvbytes += nbytes
-            for child, buf in recvs:
-                e.unpack(child, buf.data_ptr())
-                launches += 1
+                my_nodes = [n for n, own in lvl.nodes if own == rank]
+                if my_nodes:
+                    e.run_nodes(my_nodes)
+                    account()
+        self.rootOwner = plan.node_owner[0]
+        self.lastRun = dict(deviceMs=devms, kernelLaunches=launches, particleUpdates=updates, algorithmicBytes=algbytes,
+                            h2dBytes=0, d2hBytes=0, nvlinkBytes=nvbytes)
+
+    # -- population movement above the cut ----------------------------------------------------------
+    def _transport(self, dist, dev) -> str:
+        """"p2p": the owner of a node above the cut reads its remote children straight from the peer
+        GPU's pool over NVLink (CUDA IPC mapping; include/dcsmc.h "zero-copy sharing") — the product
+        path. "nccl": pack -> isend/irecv -> unpack, used when IPC is unavailable (decided once,
+        collectively), when DCSMC_TRANSPORT=nccl, and by the CPU stand-in engine of the tests."""
+        t = getattr(self, "_transportChoice", None)
+        if t is not None:
+            return t
+        import torch
+
+        want = os.environ.get("DCSMC_TRANSPORT", "p2p")
+        ok = 1 if (want == "p2p" and dev.type == "cuda" and hasattr(self.engine, "peer_pool_handle")) else 0
+        if ok:
+            try:
+                self._exchange_pool_handles(dist, dev)
+            except Exception as ex:  # IPC refused (container policy, no peer access, ...)
+                self._p2pError = str(ex)
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self._transportChoice = "p2p" if int(flag.item()) == 1 else "nccl"
+        return self._transportChoice
+
+    def _exchange_pool_handles(self, dist, dev):
+        """Every rank publishes (generation, IPC handle) of its pool; every rank maps all the others."""
+        import torch
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        handle, gen = self.engine.peer_pool_handle()
+        blk = np.zeros(8 + len(handle), np.uint8)
+        blk[:8] = np.frombuffer(np.int64(gen).tobytes(), np.uint8)
+        blk[8:] = np.frombuffer(handle, np.uint8)
+        mine = torch.from_numpy(blk).to(dev)
+        allb = torch.empty(world * blk.size, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        allb = allb.cpu().numpy().reshape(world, blk.size)
+        self._peerGen = {}
+        for r in range(world):
+            g = int(np.frombuffer(allb[r, :8].tobytes(), np.int64)[0])
+            self._peerGen[r] = g
+            if r != rank:
+                self.engine.peer_open(r, allb[r, 8:].tobytes(), g)
+
+    def _top_levels_p2p(self, dist, dev, plan, rank, world, account) -> int:
+        """Nodes above the cut, zero-copy: per level one small all-gather of export descriptors (which
+        is also the barrier that tells consumers the producers are done), then the owners run their
+        nodes reading remote children through the mapped peer pools. Exported populations stay
+        resident on the producer until the closing barrier of the run."""
+        import torch
+        from . import _ffi as F
+
+        e = self.engine
+        D = F.EXPORT_DESC_BYTES
+        if getattr(self, "_p2pLevels", None) is None or self._p2pLevelsPlan is not plan:
+            # static per plan: who exports what, in which order, and the all-gather block size
+            lv = []
+            for lvl in plan.top_levels:
+                exp = {r: [] for r in range(world)}
+                for child, src, dst in lvl.transfers:
+                    if child not in exp[src]:
+                        exp[src].append(child)
+                width = max((len(v) for v in exp.values()), default=0)
+                lv.append((exp, width))
+            self._p2pLevels, self._p2pLevelsPlan = lv, plan
+            self._p2pSync = torch.zeros(1, dtype=torch.int32, device=dev)
+        # every block starts with (generation, IPC handle) of the sender's pool: a pool that was
+        # re-allocated since the last exchange (new model, larger tree) is re-mapped on the fly
+        handle, gen = e.peer_pool_handle()
+        H = 8 + len(handle)
+        head = np.zeros(H, np.uint8)
+        head[:8] = np.frombuffer(np.int64(gen).tobytes(), np.uint8)
+        head[8:] = np.frombuffer(handle, np.uint8)
+        nvbytes = 0
+        for lvl, (exp, width) in zip(plan.top_levels, self._p2pLevels):
+            if width > 0:
+                blk = np.zeros(H + width * D, np.uint8)
+                blk[:H] = head
+                mine = exp[rank]
+                if mine:
+                    raw = e.export(mine)
+                    blk[H:H + len(raw)] = np.frombuffer(raw, np.uint8)
+                allb = torch.empty(world * blk.size, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allb, torch.from_numpy(blk).to(dev))
+                allb = allb.cpu().numpy().reshape(world, blk.size)
+                nodes, peers, descs = [], [], []
+                for child, src, dst in lvl.transfers:
+                    if dst == rank:
+                        g = int(np.frombuffer(allb[src, :8].tobytes(), np.int64)[0])
+                        if self._peerGen.get(src) != g:
+                            e.peer_open(src, allb[src, 8:H].tobytes(), g)
+                            self._peerGen[src] = g
+                        k = exp[src].index(child)
+                        nodes.append(child)
+                        peers.append(src)
+                        descs.append(allb[src, H + k * D:H + (k + 1) * D].tobytes())
+                if nodes:
+                    e.import_peer(nodes, peers, b"".join(descs))
+                    # bytes the merge kernel pulls over NVLink: ancestors + the columns it reads
+                    nvbytes += sum(self._peer_read_bytes(c) for c in nodes)
             my_nodes = [n for n, own in lvl.nodes if own == rank]
             if my_nodes:
                 e.run_nodes(my_nodes)
                 account()
-        self.rootOwner = plan.node_owner[0]
-        self.lastRun = dict(deviceMs=devms, kernelLaunches=launches, particleUpdates=updates, algorithmicBytes=algbytes,
-                            h2dBytes=0, d2hBytes=0, nvlinkBytes=nvbytes)
+        # nobody may start overwriting its pool (next run) while a peer still reads from it
+        dist.all_reduce(self._p2pSync)
+        torch.cuda.current_stream(dev).synchronize()
+        return nvbytes
+
+    def _peer_read_bytes(self, child: int) -> int:
+        N = self.options.nParticles
+        internal = self.csr.nChildren(child) > 0
+        markov = isinstance(self.proposalFactory, MarkovChainNaiveProposalFactory)
+        if markov:
+            return N * 8
+        return N * (4 + 8 * (5 if internal else 2))
 
     @property
     def stats(self) -> Dict[str, np.ndarray]:

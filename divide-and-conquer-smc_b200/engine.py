@@ -144,6 +144,30 @@ class Engine:
     def unpack(self, node: int, device_ptr: int):
         self._ck(self._L.dcsmc_population_unpack(self._h, node, C.c_void_p(device_ptr)))
 
+    # -- zero-copy sharing over NVLink peer memory (CUDA IPC) ---------------------------------------
+    def peer_pool_handle(self):
+        """(64-byte IPC handle of this engine's pool, pool generation)"""
+        h = (C.c_char * F.IPC_HANDLE_BYTES)()
+        gen = C.c_int64()
+        self._ck(self._L.dcsmc_peer_pool_handle(self._h, h, C.byref(gen)))
+        return bytes(h), gen.value
+
+    def peer_open(self, peer: int, handle: bytes, generation: int):
+        buf = (C.c_char * F.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        self._ck(self._L.dcsmc_peer_open(self._h, peer, buf, generation))
+
+    def export(self, nodes: Sequence[int]) -> bytes:
+        r = np.ascontiguousarray(nodes, dtype=np.int32)
+        out = (C.c_char * (F.EXPORT_DESC_BYTES * max(1, len(r))))()
+        self._ck(self._L.dcsmc_population_export(self._h, _ptr(r, C.c_int32), len(r), out))
+        return bytes(out)[:F.EXPORT_DESC_BYTES * len(r)]
+
+    def import_peer(self, nodes: Sequence[int], peers: Sequence[int], descs: bytes):
+        r = np.ascontiguousarray(nodes, dtype=np.int32)
+        q = np.ascontiguousarray(peers, dtype=np.int32)
+        buf = (C.c_char * max(1, len(descs))).from_buffer_copy(descs if descs else b"\0")
+        self._ck(self._L.dcsmc_population_import_peer(self._h, _ptr(r, C.c_int32), _ptr(q, C.c_int32), len(r), buf))
+
     def reset_populations(self):
         self._ck(self._L.dcsmc_reset_populations(self._h))
 
@@ -154,6 +178,14 @@ class Engine:
         r = F.RunInfo()
         self._ck(self._L.dcsmc_last_run_info(self._h, C.byref(r)))
         return r
+
+    def timer_begin(self):
+        self._ck(self._L.dcsmc_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        self._ck(self._L.dcsmc_timer_end(self._h, C.byref(ms)))
+        return ms.value
 
     def profile_enable(self, on: bool = True):
         self._ck(self._L.dcsmc_profile_enable(self._h, 1 if on else 0))

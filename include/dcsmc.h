@@ -200,6 +200,27 @@ int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node);
  * dcsmc_run_subtrees / dcsmc_run_nodes use it between independent executions) */
 int32_t dcsmc_reset_populations(dcsmc_engine* e);
 
+/* ---- zero-copy sharing between the engines of one NVLink/NVSwitch node ----------------------
+ * Instead of pack -> send -> unpack, the consuming engine maps the producing engine's population
+ * pool (CUDA IPC) and its merge kernel reads the child's columns — through the child's ancestor
+ * indices, i.e. the gather of the resampled population is fused into the NVLink read — directly
+ * from peer memory. Replaces the same Hazelcast put/remove (DCRecursionTask.java:37,113); only
+ * DCSMC_EXPORT_DESC_BYTES per population cross the host. The producer must keep the population
+ * resident (no release, no new run) until the consumer's run call has returned. */
+#define DCSMC_IPC_HANDLE_BYTES 64
+#define DCSMC_EXPORT_DESC_BYTES 128
+/* IPC handle of this engine's pool (allocates it if needed) and the pool's generation (changes
+ * whenever the pool is re-allocated; peers must then re-open) */
+int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generation);
+/* map a peer engine's pool (no-op if that generation is already mapped) */
+int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64_t generation);
+/* descriptors (n * DCSMC_EXPORT_DESC_BYTES host bytes) of finished, resident populations */
+int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* descs);
+/* install peer-resident populations as the finished populations of `nodes` (peers[k] = the id
+ * given to dcsmc_peer_open for the owner of nodes[k]) */
+int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, const int32_t* peers,
+                                     int32_t n, const void* descs);
+
 /* ---- measurement ---------------------------------------------------------------------- */
 
 enum {
@@ -228,6 +249,11 @@ typedef struct dcsmc_run_info {
 } dcsmc_run_info;
 
 int32_t dcsmc_last_run_info(const dcsmc_engine* e, dcsmc_run_info* out);
+
+/* CUDA events on the engine's launching stream, bracketing any sequence of calls on this engine
+ * (bench.py: K whole runs incl. the gaps between them). deviceMs of dcsmc_run_info covers one call. */
+int32_t dcsmc_timer_begin(dcsmc_engine* e);
+int32_t dcsmc_timer_end(dcsmc_engine* e, double* ms);
 
 /* per-kernel-class CUDA-event timing (adds an event pair around every launch) */
 int32_t dcsmc_profile_enable(dcsmc_engine* e, int32_t enable);

@@ -28,7 +28,16 @@ def wrap(name):
     def g(*a, **k):
         t0 = time.perf_counter(); r = f(*a, **k); T[name] = T.get(name, 0) + time.perf_counter() - t0; return r
     setattr(E, name, g)
-for n in ["run_subtrees", "run_nodes", "pack", "unpack", "all_node_stats", "reset_populations", "release"]: wrap(n)
+for n in ["run_subtrees", "run_nodes", "pack", "unpack", "all_node_stats", "reset_populations", "release",
+          "export", "import_peer", "peer_pool_handle"]: wrap(n)
+_ag = dist.all_gather_into_tensor
+def ag(*a, **k):
+    t0 = time.perf_counter(); r = _ag(*a, **k); torch.cuda.current_stream().synchronize(); T["all_gather"] = T.get("all_gather", 0) + time.perf_counter() - t0; return r
+dist.all_gather_into_tensor = ag
+_ar = dist.all_reduce
+def ar(*a, **k):
+    t0 = time.perf_counter(); r = _ar(*a, **k); torch.cuda.current_stream().synchronize(); T["all_reduce"] = T.get("all_reduce", 0) + time.perf_counter() - t0; return r
+dist.all_reduce = ar
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.perf_counter()
 for _ in range(5): ddc.run()
