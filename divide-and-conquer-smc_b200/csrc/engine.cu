@@ -57,6 +57,10 @@ struct CachedPlan {
   std::vector<char> resident, imported;
   std::vector<char> inPlan;  // per node: computed by this plan
   std::vector<int> finalResident;  // nodes still resident when the plan has run (its roots, unless retained)
+  // the plan's whole launch sequence as a CUDA graph (captured on its first replay)
+  mutable cudaGraphExec_t graphExec = nullptr;
+  mutable uint64_t graphScratchGen = 0;
+  mutable dcsmc_run_info graphInfo{};
 };
 
 }  // namespace
@@ -70,7 +74,9 @@ struct dcsmc_engine {
   std::vector<cudaEvent_t> evPool;  // untimed events ordering the two streams
   size_t evNext = 0;
   int smCount = 148;
-  int overlapChunks = 1;            // level batches are split in this many chunks (1 = one stream)
+  int overlapChunks = 1;
+  bool useGraphs = true;       // replay cached plans as CUDA graphs (DCSMC_GRAPHS=0 disables)
+  uint64_t scratchGen = 1;     // bumped when a scratch buffer baked into captured launches moves            // level batches are split in this many chunks (1 = one stream)
 
   // topology / model (host)
   int nNodes = 0, root = 0;
@@ -358,6 +364,13 @@ int ensureDevice(dcsmc_engine* e) {
 }
 
 // (re)build the device-side tables that do not depend on the memory plan
+void clearPlanCache(dcsmc_engine* e) {
+  for (CachedPlan& cp : e->planCache)
+    if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec);
+  e->planCache.clear();
+  e->devicePlan = nullptr;
+}
+
 int uploadTables(dcsmc_engine* e) {
   if (!e->tablesDirty) return DCSMC_OK;
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
@@ -409,7 +422,7 @@ int uploadTables(dcsmc_engine* e) {
   e->slot.assign(nN, Slot{});
   e->poolNeed = 0;
   e->descDirty.clear();
-  e->planCache.clear();
+  clearPlanCache(e);
   e->devicePlan = nullptr;
   e->resident.assign(nN, 0);
   e->imported.assign(nN, 0);
@@ -859,6 +872,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     *p = nullptr;
     cudaError_t r = cudaMalloc(p, need * elem);
     cap = r == cudaSuccess ? need : 0;
+    e->scratchGen++;
     return r;
   };
   CK(grow((void**)&e->dCdf, e->cdfCap, std::max<size_t>(1, maxInternalStep * (size_t)e->Npad), sizeof(double)));
@@ -880,6 +894,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
       CK(cudaMalloc((void**)&buf, plan.stepNodes.size() * sizeof(int32_t)));
       cap = plan.stepNodes.size();
       descriptorsOnDevice = false;
+      e->scratchGen++;
     }
     e->curStepNodes = buf;
     if (!descriptorsOnDevice)
@@ -902,58 +917,99 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     if (cached != nullptr) e->devicePlan = cached;
   }
   CKPOINT("descriptor upload");
-  // accumulators of the nodes about to be recomputed start from zero
-  if (!plan.stepNodes.empty()) {
-    const int n = (int)plan.stepNodes.size();
-    k_reset_stats<<<(n + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->curStepNodes, n);
-    CK(cudaGetLastError());
-  }
   RunCtx c;
   makeCtx(e, c);
   e->info = dcsmc_run_info{};
   e->info.poolBytes = (int64_t)e->poolBytes;
   e->info.h2dBytes = e->pendingH2D + (descriptorsOnDevice ? 0 : (int64_t)(plan.stepNodes.size() * sizeof(int32_t) + sizeof(NodeDev) * e->nNodes));
   e->pendingH2D = 0;
-  CK(cudaEventRecord(e->ev0, e->stream));
   // level batches, each cut into chunks whose chains overlap the next chunk's propose kernel
   const bool overlap = !e->profile && e->overlapChunks > 1 && e->streamR != nullptr;
-  e->evNext = 0;
-  cudaEvent_t chainDone = nullptr;  // last chain work of the previous level batch
-  for (auto& s : plan.steps) {
-    int nCh = 1;
-    if (overlap) nCh = std::max(1, std::min({e->overlapChunks, MAX_CHUNKS, s.count / 8}));
-    if (chainDone) {  // children must be complete (and the scratch free) before this level starts
-      CK(cudaStreamWaitEvent(e->stream, chainDone, 0));
-      chainDone = nullptr;
+  auto launchAll = [&]() -> int {
+    // accumulators of the nodes about to be recomputed start from zero
+    if (!plan.stepNodes.empty()) {
+      const int n = (int)plan.stepNodes.size();
+      k_reset_stats<<<(n + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->curStepNodes, n);
+      CK(cudaGetLastError());
     }
-    for (int k = 0; k < nCh; ++k) {
-      const int lo = (int)((long long)s.count * k / nCh), hi = (int)((long long)s.count * (k + 1) / nCh);
-      Step sub;
-      sub.offset = s.offset + lo;
-      sub.count = hi - lo;
-      sub.leaf = s.leaf;
-      const ChunkCtx ch{e->stream, nCh > 1 ? e->streamR : e->stream, lo, k};
-      switch (e->opt.rngMode) {
-        case DCSMC_RNG_PHILOX: rc = launchStep<RNG_PHILOX>(e, c, sub, ch); break;
-        case DCSMC_RNG_INJECTED: rc = launchStep<RNG_INJECTED>(e, c, sub, ch); break;
-        default: rc = launchStep<RNG_JAVA>(e, c, sub, ch); break;
+    e->evNext = 0;
+    cudaEvent_t chainDone = nullptr;  // last chain work of the previous level batch
+    for (auto& s : plan.steps) {
+      int nCh = 1;
+      if (overlap) nCh = std::max(1, std::min({e->overlapChunks, MAX_CHUNKS, s.count / 8}));
+      if (chainDone) {  // children must be complete (and the scratch free) before this level starts
+        CK(cudaStreamWaitEvent(e->stream, chainDone, 0));
+        chainDone = nullptr;
       }
-      if (rc) return rc;
+      for (int k = 0; k < nCh; ++k) {
+        const int lo = (int)((long long)s.count * k / nCh), hi = (int)((long long)s.count * (k + 1) / nCh);
+        Step sub;
+        sub.offset = s.offset + lo;
+        sub.count = hi - lo;
+        sub.leaf = s.leaf;
+        const ChunkCtx ch{e->stream, nCh > 1 ? e->streamR : e->stream, lo, k};
+        int rc2;
+        switch (e->opt.rngMode) {
+          case DCSMC_RNG_PHILOX: rc2 = launchStep<RNG_PHILOX>(e, c, sub, ch); break;
+          case DCSMC_RNG_INJECTED: rc2 = launchStep<RNG_INJECTED>(e, c, sub, ch); break;
+          default: rc2 = launchStep<RNG_JAVA>(e, c, sub, ch); break;
+        }
+        if (rc2) return rc2;
+      }
+      if (nCh > 1) {
+        chainDone = nextEvent(e);
+        CK(cudaEventRecord(chainDone, e->streamR));
+      }
+      e->info.levelBatches++;
+      e->info.nodesProcessed += s.count;
+      for (int k = 0; k < s.count; ++k) {
+        const int n = plan.stepNodes[s.offset + k];
+        const int64_t C = nChildrenOf(e, n);
+        e->info.algorithmicBytes +=
+            (int64_t)N * (40 * C + 184 + (e->opt.resamplingScheme == DCSMC_MULTINOMIAL ? 16 : 0));
+      }
     }
-    if (nCh > 1) {
-      chainDone = nextEvent(e);
-      CK(cudaEventRecord(chainDone, e->streamR));
+    if (chainDone) CK(cudaStreamWaitEvent(e->stream, chainDone, 0));
+    return DCSMC_OK;
+  };
+  // A cached plan whose descriptors are already on the device is a fixed launch sequence: it is
+  // captured once into a CUDA graph and replayed with one launch (no per-kernel launch gaps; this
+  // matters for small populations and for the short per-GPU runs of a sharded tree).
+  const bool useGraph = e->useGraphs && cached != nullptr && descriptorsOnDevice && !e->profile && !overlap;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  if (useGraph) {
+    if (cached->graphExec != nullptr && cached->graphScratchGen != e->scratchGen) {
+      cudaGraphExecDestroy(cached->graphExec);
+      cached->graphExec = nullptr;
     }
-    e->info.levelBatches++;
-    e->info.nodesProcessed += s.count;
-    for (int k = 0; k < s.count; ++k) {
-      const int n = plan.stepNodes[s.offset + k];
-      const int64_t C = nChildrenOf(e, n);
-      e->info.algorithmicBytes +=
-          (int64_t)N * (40 * C + 184 + (e->opt.resamplingScheme == DCSMC_MULTINOMIAL ? 16 : 0));
+    if (cached->graphExec == nullptr) {
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      rc = launchAll();
+      const cudaError_t endErr = cudaStreamEndCapture(e->stream, &g);
+      if (rc) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+      if (endErr != cudaSuccess) return e->fail(DCSMC_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(endErr));
+      const cudaError_t instErr = cudaGraphInstantiate(&cached->graphExec, g, 0);
+      cudaGraphDestroy(g);
+      if (instErr != cudaSuccess) {
+        cached->graphExec = nullptr;
+        return e->fail(DCSMC_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(instErr));
+      }
+      cached->graphScratchGen = e->scratchGen;
+      cached->graphInfo = e->info;
+    } else {
+      e->info.kernelLaunches = cached->graphInfo.kernelLaunches;
+      e->info.levelBatches = cached->graphInfo.levelBatches;
+      e->info.nodesProcessed = cached->graphInfo.nodesProcessed;
+      e->info.algorithmicBytes = cached->graphInfo.algorithmicBytes;
     }
+    CK(cudaGraphLaunch(cached->graphExec, e->stream));
+  } else {
+    if ((rc = launchAll())) return rc;
   }
-  if (chainDone) CK(cudaStreamWaitEvent(e->stream, chainDone, 0));
   CK(cudaEventRecord(e->ev1, e->stream));
   CKPOINT("level batches");
   // fetch the statistics of the nodes this plan computed: compact records, pinned staging
@@ -1131,6 +1187,7 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   if (cudaSetDevice(opt->device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
   cudaDeviceGetAttribute(&e->smCount, cudaDevAttrMultiProcessorCount, opt->device);
   if (e->smCount <= 0) e->smCount = 148;
+  if (const char* v = getenv("DCSMC_GRAPHS")) e->useGraphs = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_OVERLAP_CHUNKS")) e->overlapChunks = std::max(1, atoi(v));
   if (cudaSetDevice(opt->device) != cudaSuccess ||
       cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prLow) != cudaSuccess ||
@@ -1188,7 +1245,9 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->streamR) cudaStreamDestroy(e->streamR);
   for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
-  chk("streams and events");
+  for (CachedPlan& cp : e->planCache)
+    if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec);
+  chk("streams, events, graphs");
   delete e;
   return DCSMC_OK;
 }
