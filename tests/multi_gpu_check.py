@@ -48,7 +48,26 @@ def main():
                 tot = torch.tensor([moved], device="cuda", dtype=torch.float64)
                 dist.all_reduce(tot)
                 assert tot.item() > 0, "nothing crossed NVLink"
+                transport = ddc._transportChoice
                 ddc.close()
+    # the reference's own example model (Doc.java:162-237) through the same sharded path
+    from test_gpu_dc_api import transition, prior
+
+    tree = d.perfectBinaryTree(4)
+    for thr in (1.0 + 1e-10, 0.5):
+        opt = d.DCOptions(nParticles=N, relativeEssThreshold=thr, maximumDistributionDepth=2)
+        ddc = d.DistributedDC.createInstance(opt, d.MarkovChainNaiveProposalFactory(transition, prior), tree, device=local)
+        ddc.start()
+        sharded_m = {k: v.copy() for k, v in ddc.stats.items()}
+        root = ddc.getRootPopulation().particles.copy() if rank == ddc.rootOwner else None
+        ddc.engine.run()
+        single = ddc.engine.all_node_stats()
+        for k in ("ess", "relEss", "logNormEstimate", "logScaling", "resampled"):
+            assert np.array_equal(sharded_m[k], single[k]), ("markov", thr, k)
+        if root is not None:
+            _, ist, _ = ddc.engine.population(0, state=False, istate=True)
+            assert np.array_equal(root, ist)
+        ddc.close()
     if rank == 0:
         import oracle_lib as o
 
@@ -57,7 +76,7 @@ def main():
         ref = o.run(csr, N, resamplingScheme=o.STRATIFIED, relativeEssThreshold=0.6, rngMode=o.RNG_PHILOX,
                     sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
         assert np.array_equal(ref.logNormEstimate, sharded["logNormEstimate"])
-        print("MULTI_GPU_CHECK_OK world", world)
+        print("MULTI_GPU_CHECK_OK world", world, "transport", transport)
     dist.barrier()
     dist.destroy_process_group()
 

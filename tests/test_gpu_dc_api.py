@@ -133,15 +133,19 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_sharded_run_is_bit_identical_to_single_gpu(world):
+@pytest.mark.parametrize("world,transport", [(2, "p2p"), (2, "nccl"), (4, "p2p")])
+def test_sharded_run_is_bit_identical_to_single_gpu(world, transport):
+    """p2p: owners above the cut read remote children through CUDA-IPC mapped peer pools (the product
+    path); nccl: pack -> isend/irecv -> unpack (fallback). Both must reproduce the 1-GPU run bit for bit."""
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ, DCSMC_TRANSPORT=transport)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI_GPU_CHECK_OK" in r.stdout
+    assert f"transport {transport}" in r.stdout, r.stdout[-500:]
 
 
 def test_native_cli_run_matches_engine(tmp_path):

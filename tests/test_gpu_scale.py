@@ -171,3 +171,61 @@ def test_observed_leaves_not_materialised_same_results(scheme):
         rs, _, rw = e.population(0)
         assert np.array_equal(rs, ref.rootState, equal_nan=True)
         assert np.array_equal(rw, ref.rootWeights)
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_graph_replay_and_chunked_streams_do_not_change_results(scheme, monkeypatch):
+    """A cached plan is replayed as a CUDA graph from its second execution on; DCSMC_OVERLAP_CHUNKS
+    splits every level over two streams. Neither may change a single bit (per-node streams, exact sums)."""
+    csr, nT, nS = dataset(synth.wide_rows(7, [5, 6, 4]))
+    N = 30000
+
+    def run(env):
+        for k in ("DCSMC_GRAPHS", "DCSMC_OVERLAP_CHUNKS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Engine(nParticles=N, resamplingScheme=scheme, relativeEssThreshold=0.7) as e:
+            e.set_tree(csr)
+            e.set_multilevel_model(nT, nS)
+            out = []
+            for _ in range(3):  # 1st: planned, 2nd: graph captured, 3rd: graph replayed
+                e.run()
+                st = e.all_node_stats()
+                rs, _, rw = e.population(0)
+                out.append((st, rs, rw, e.run_info().kernelLaunches))
+            return out
+
+    base = run({"DCSMC_GRAPHS": "0"})
+    graphs = run({"DCSMC_GRAPHS": "1"})
+    chunks = run({"DCSMC_OVERLAP_CHUNKS": "4"})
+    for other in (graphs, chunks):
+        for (st0, rs0, rw0, _), (st1, rs1, rw1, _) in zip(base, other):
+            for k in st0:
+                assert np.array_equal(st0[k], st1[k]), k
+            assert np.array_equal(rs0, rs1, equal_nan=True) and np.array_equal(rw0, rw1)
+    assert graphs[0][3] == graphs[2][3] == base[0][3] > 0  # launch accounting survives the replay
+
+
+def test_engine_stream_timer_and_export_error_paths():
+    from dcsmc_b200 import _ffi
+
+    csr, nT, nS = dataset(synth.small_multilevel_rows())
+    with Engine(nParticles=2048) as e:
+        with pytest.raises(_ffi.DcsmcError):
+            e.timer_end()  # no timer_begin yet
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.timer_begin()
+        e.run()
+        e.run()
+        ms = e.timer_end()
+        assert ms >= e.run_info().deviceMs > 0
+        desc = e.export([0])  # the root is resident after a run
+        assert len(desc) == _ffi.EXPORT_DESC_BYTES
+        with pytest.raises(_ffi.DcsmcError):
+            e.export([1])  # consumed by its parent: not resident
+        with pytest.raises(_ffi.DcsmcError):
+            e.import_peer([1], [3], desc)  # peer 3 was never mapped with dcsmc_peer_open
+        handle, gen = e.peer_pool_handle()
+        assert len(handle) == _ffi.IPC_HANDLE_BYTES and gen >= 1
