@@ -20,6 +20,7 @@ from .dc import (  # noqa: F401,E402
     DCProcessorFactoryContext,
     DCProposalFactory,
     DefaultProcessorFactory,
+    PosteriorSummaryProcessorFactory,
     DistributedDC,
     GaussianLeafProposalFactory,
     MarkovChainNaiveProposalFactory,

@@ -35,8 +35,10 @@ class Options(C.Structure):
         ("sumMode", C.c_int32),
         ("maxBetaAttempts", C.c_int32),
         ("retainPopulations", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("levelCutOffForOutput", C.c_int32),
         ("memoryBudgetBytes", C.c_int64),
+        ("useTransform", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -48,6 +50,15 @@ class NodeStats(C.Structure):
         ("logScaling", C.c_double),
         ("resampled", C.c_int32),
         ("done", C.c_int32),
+    ]
+
+
+class NodeSummary(C.Structure):
+    _fields_ = [
+        ("meanMean", C.c_double), ("meanSD", C.c_double),
+        ("varMean", C.c_double), ("varSD", C.c_double),
+        ("deltaMean", C.c_double), ("deltaSD", C.c_double),
+        ("hasMean", C.c_int32), ("hasVar", C.c_int32), ("hasDelta", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -76,7 +87,7 @@ SYMBOLS = [
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
     "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval", "dcsmc_reset_populations",
     "dcsmc_timer_begin", "dcsmc_timer_end",
-    "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
+    "dcsmc_node_summary", "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
 ]
 IPC_HANDLE_BYTES, EXPORT_DESC_BYTES = 64, 128
 
@@ -121,6 +132,7 @@ def lib():
     L.dcsmc_population_release.argtypes = [vp, i32]
     L.dcsmc_reset_populations.argtypes = [vp]
     L.dcsmc_last_run_info.argtypes = [vp, P(RunInfo)]
+    L.dcsmc_node_summary.argtypes = [vp, i32, P(NodeSummary)]
     L.dcsmc_peer_pool_handle.argtypes = [vp, vp, P(i64)]
     L.dcsmc_peer_open.argtypes = [vp, i32, vp, i64]
     L.dcsmc_population_export.argtypes = [vp, P(i32), i32, vp]

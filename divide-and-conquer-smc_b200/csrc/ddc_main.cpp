@@ -146,6 +146,8 @@ void usage() {
       "        [-maximumDistributionDepth <int>] [-nThreadsPerNode 1] [-variancePrior 1.0]\n"
       "        [-clusterSubGroup 1] [-minimumNumberOfClusterMembersToStart 1] [-maximumTimeToWaitInMinutes 1]\n"
       "        [-indexInCluster 1] [-device 0] [-resultsFolder results/latest] [-dumpTree]\n"
+      "        [-levelCutOffForOutput 0] [-useTransform true]   (posterior summaries of impl-1: meanStats,\n"
+      "        varStats, deltaStats for nodes with level < cut-off; the reference's default cut-off is 2)\n"
       "flags are the field names of dc.DCOptions / MultiLevelProposalFactory (dc/DDCMain.java:14-18)");
 }
 
@@ -182,6 +184,9 @@ int main(int argc, char** argv) {
     else if (a == "maximumTimeToWaitInMinutes") opt.maximumTimeToWaitInMinutes = std::atoi(val());
     else if (a == "indexInCluster") opt.indexInCluster = std::atoi(val());
     else if (a == "device") opt.device = std::atoi(val());
+    // impl-1 output options (prototype/smc/DivideConquerMCAlgorithm.java:47,56)
+    else if (a == "levelCutOffForOutput") opt.levelCutOffForOutput = std::atoi(val());
+    else if (a == "useTransform") opt.useTransform = std::string(val()) != "false";
     else if (a == "resamplingScheme") {
       const std::string v = val();
       if (v == "MULTINOMIAL") opt.resamplingScheme = DCSMC_MULTINOMIAL;
@@ -248,6 +253,32 @@ int main(int argc, char** argv) {
     if (nN <= 64 || i == 0)
       std::printf("timing: node=%s, ESS=%.17g, rESS=%.17g, logZ=%.17g, nWorkers=1, iterationProposalTime=%.3f, globalTime=%.3f\n",
                   name.c_str(), st[i].ess, st[i].relEss, st[i].logNormEstimate, info.deviceMs / nN, globalMs);
+  }
+  if (opt.levelCutOffForOutput > 0) {
+    // printNodeStatistics / printDeltaNodeStatistics tables (DivideConquerMCAlgorithm.java:433-507)
+    std::ofstream meanStats(results + "/meanStats.csv"), varStats(results + "/varStats.csv"),
+        deltaStats(results + "/deltaStats.csv");
+    meanStats << "path,meanMean,meanSD\n";
+    varStats << "path,varMean,varSD\n";
+    deltaStats << "path,deltaMean,deltaSD\n";
+    for (int i : order) {
+      if ((int)t.path[i].size() - 1 > opt.levelCutOffForOutput) continue;  // deltas sit one level below the cut
+      dcsmc_node_summary_t s;
+      if (dcsmc_node_summary(e, i, &s) != DCSMC_OK) continue;
+      const std::string name = joinPath(t.path[i], t.path[i].size(), '-');
+      if (s.hasMean) {
+        std::snprintf(buf, sizeof buf, "%s,%.17g,%.17g", name.c_str(), s.meanMean, s.meanSD);
+        meanStats << buf << "\n";
+      }
+      if (s.hasVar) {
+        std::snprintf(buf, sizeof buf, "%s,%.17g,%.17g", name.c_str(), s.varMean, s.varSD);
+        varStats << buf << "\n";
+      }
+      if (s.hasDelta) {
+        std::snprintf(buf, sizeof buf, "%s,%.17g,%.17g", name.c_str(), s.deltaMean, s.deltaSD);
+        deltaStats << buf << "\n";
+      }
+    }
   }
   std::snprintf(buf, sizeof buf, "%.17g", st[0].logNormEstimate);
   std::ofstream(results + "/logZ") << buf;

@@ -100,6 +100,7 @@ struct dcsmc_engine {
   int32_t* dStepNodesTmp = nullptr;  // step lists of the current uncached plan
   size_t stepNodesTmpCap = 0;
   int32_t* curStepNodes = nullptr;   // the one the running plan uses
+  const int32_t* planStepNodes = nullptr;  // host copy of the same lists (valid while a plan executes)
   double** dInj = nullptr;
   uint64_t* dJavaState = nullptr;
   double *dMarkovT = nullptr, *dMarkovPrior = nullptr;
@@ -133,6 +134,12 @@ struct dcsmc_engine {
   size_t exportCap = 0;
   cudaEvent_t evT0 = nullptr, evT1 = nullptr;           // dcsmc_timer_begin / dcsmc_timer_end
   int Npad = 0;
+
+  // posterior summaries (levelCutOffForOutput > 0)
+  std::vector<int32_t> depth;        // level() of every node
+  NodeSummary* dSumm = nullptr;      // per node
+  double* dSumScratch = nullptr;     // sample series of one summary batch
+  size_t sumScratchCap = 0;          // in doubles
 
   // scratch
   double* dCdf = nullptr;
@@ -383,6 +390,10 @@ int uploadTables(dcsmc_engine* e) {
   };
   CK(re((void**)&e->dNodes, sizeof(NodeDev) * nN));
   CK(re((void**)&e->dStats, sizeof(NodeStats) * nN));
+  if (e->opt.levelCutOffForOutput > 0) {
+    CK(re((void**)&e->dSumm, sizeof(NodeSummary) * nN));
+    CK(cudaMemsetAsync(e->dSumm, 0, sizeof(NodeSummary) * nN, e->stream));
+  }
   CK(re((void**)&e->dLeaf, sizeof(LeafConst) * nN));
   CK(re((void**)&e->dChildren, sizeof(int32_t) * std::max<size_t>(1, e->children.size())));
   CK(re((void**)&e->dInj, sizeof(double*) * nN));
@@ -661,6 +672,72 @@ size_t descWordsPerNode(int N) {
 }
 constexpr int MAX_CHUNKS = 16;
 
+// Sample series a summary node writes: mean, variance (internal nodes), one delta per child when
+// the node's children are still below the cut-off (DivideConquerMCAlgorithm.java:423-428).
+bool summaryReportsDeltas(const dcsmc_engine* e, int n) {
+  return e->depth[n] + 1 < e->opt.levelCutOffForOutput && nChildrenOf(e, n) > 0;
+}
+int summarySeries(const dcsmc_engine* e, int n) {
+  return 1 + (nodeKind(e, n) == KIND_INTERNAL ? 1 : 0) + (summaryReportsDeltas(e, n) ? nChildrenOf(e, n) : 0);
+}
+// uniforms of a node's summary stream (injected mode): 2 per attempt, maxAtt attempts, 2+C draws per particle
+int64_t summaryUniforms(const dcsmc_engine* e, int n) {
+  if (e->opt.levelCutOffForOutput <= 0 || e->model != DCSMC_MODEL_MULTILEVEL || e->depth.empty() ||
+      e->depth[n] >= e->opt.levelCutOffForOutput)
+    return 0;
+  return (int64_t)e->opt.nParticles * (2 + nChildrenOf(e, n)) * e->opt.maxBetaAttempts * 2;
+}
+
+// Posterior summaries of the step's nodes above the output cut-off, right after their node step
+// (their children are still resident). Batches of <= SUM_BATCH nodes, passed to the kernels by value.
+template <int RNG>
+int launchSummaries(dcsmc_engine* e, RunCtx& c, const Step& st, cudaStream_t s) {
+  if (e->opt.levelCutOffForOutput <= 0 || e->model != DCSMC_MODEL_MULTILEVEL || e->dSumm == nullptr) return DCSMC_OK;
+  const int* nodes = e->planStepNodes + st.offset;
+  const int N = c.N;
+  const int tilesP = (N + PROPOSE_THREADS - 1) / PROPOSE_THREADS;
+  const size_t maxSeries = std::max<size_t>(64, ((size_t)1 << 28) / (size_t)c.Npad);  // <= 2 GiB of samples per batch
+  int k = 0;
+  while (k < st.count) {
+    SumBatch b;
+    memset(&b, 0, sizeof b);
+    int series = 0;
+    for (; k < st.count && b.n < SUM_BATCH; ++k) {
+      const int n = nodes[k];
+      if (e->depth[n] >= e->opt.levelCutOffForOutput) continue;
+      const int ns = summarySeries(e, n);
+      if (b.n > 0 && (size_t)(series + ns) > maxSeries) break;
+      b.node[b.n] = n;
+      b.base[b.n] = series;
+      b.delta[b.n] = summaryReportsDeltas(e, n) ? 1 : 0;
+      series += ns;
+      b.n++;
+    }
+    if (b.n == 0) continue;
+    b.base[b.n] = series;
+    const size_t need = (size_t)series * c.Npad;
+    if (need > e->sumScratchCap) {  // first (uncaptured) execution of a plan sizes the scratch
+      if (e->dSumScratch) cudaFree(e->dSumScratch);
+      e->dSumScratch = nullptr;
+      e->sumScratchCap = 0;
+      CK(cudaMalloc((void**)&e->dSumScratch, need * sizeof(double)));
+      e->sumScratchCap = need;
+      e->scratchGen++;
+    }
+    c.sumScratch = e->dSumScratch;
+    {
+      ProfScope p(e, DCSMC_K_GATHER, s);
+      k_summary_samples<RNG><<<(unsigned)(b.n * tilesP), PROPOSE_THREADS, 0, s>>>(c, b, tilesP);
+    }
+    {
+      ProfScope p(e, DCSMC_K_GATHER, s);
+      k_summary_reduce<<<(unsigned)series, SUMRED_THREADS, 0, s>>>(c, b);
+    }
+    CK(cudaGetLastError());
+  }
+  return DCSMC_OK;
+}
+
 template <int RNG>
 int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkCtx& ch) {
   RunCtx c = base;
@@ -725,10 +802,12 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
       CK(cudaFuncSetAttribute(k_node_small<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       e->smallSmemSet[RNG] = smem;
     }
-    ProfScope p(e, DCSMC_K_SCAN, sR);
-    k_node_small<RNG><<<st.count, SMALLN_THREADS, smem, sR>>>(c);
+    {
+      ProfScope p(e, DCSMC_K_SCAN, sR);
+      k_node_small<RNG><<<st.count, SMALLN_THREADS, smem, sR>>>(c);
+    }
     CK(cudaGetLastError());
-    return DCSMC_OK;
+    return launchSummaries<RNG>(e, c, st, sR);
   }
   if (st.leaf) {
     // all weights equal: the exact sums are known in closed form, no scan and no CDF
@@ -785,7 +864,7 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     }
   }
   CK(cudaGetLastError());
-  return DCSMC_OK;
+  return launchSummaries<RNG>(e, c, st, sR);
 }
 
 int makeCtx(dcsmc_engine* e, RunCtx& c) {
@@ -818,12 +897,22 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.javaSums = e->opt.sumMode == DCSMC_SUM_JAVA;
   c.skipObs = skipObservedLeaves(e);
   c.uniformLogW = uniformLeafLogW(e);
+  c.summ = e->dSumm;
+  c.sumScratch = e->dSumScratch;
+  c.useTransform = e->opt.useTransform;
   return DCSMC_OK;
 }
 
 int validateForRun(dcsmc_engine* e) {
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
   if (e->model < 0) return e->fail(DCSMC_ESTATE, "no proposal model set (dcsmc_set_*_model)");
+  if (e->opt.levelCutOffForOutput > 0 && e->model == DCSMC_MODEL_MULTILEVEL) {
+    if (e->opt.rngMode == DCSMC_RNG_JAVA)
+      return e->fail(DCSMC_EINVAL, "levelCutOffForOutput needs a slot-addressed stream (Philox or injected): "
+                                   "nextGaussian consumes a data-dependent number of draws");
+    if (e->opt.sumMode == DCSMC_SUM_JAVA)
+      return e->fail(DCSMC_EINVAL, "levelCutOffForOutput is not available in the DCSMC_SUM_JAVA parity mode");
+  }
   if (e->opt.rngMode == DCSMC_RNG_JAVA) {
     if (e->javaHash.empty()) return e->fail(DCSMC_ESTATE, "DCSMC_RNG_JAVA needs dcsmc_set_node_seeds");
     if (e->model == DCSMC_MODEL_MULTILEVEL)
@@ -917,6 +1006,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     if (cached != nullptr) e->devicePlan = cached;
   }
   CKPOINT("descriptor upload");
+  e->planStepNodes = plan.stepNodes.data();
   RunCtx c;
   makeCtx(e, c);
   e->info = dcsmc_run_info{};
@@ -929,7 +1019,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     // accumulators of the nodes about to be recomputed start from zero
     if (!plan.stepNodes.empty()) {
       const int n = (int)plan.stepNodes.size();
-      k_reset_stats<<<(n + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->curStepNodes, n);
+      k_reset_stats<<<(n + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->dSumm, e->curStepNodes, n);
       CK(cudaGetLastError());
     }
     e->evNext = 0;
@@ -1150,6 +1240,8 @@ int32_t dcsmc_options_default(dcsmc_options* o) {
   o->sumMode = DCSMC_SUM_EXACT;
   o->maxBetaAttempts = 32;
   o->retainPopulations = 0;
+  o->levelCutOffForOutput = 0;  // reference default 2 (DivideConquerMCAlgorithm.java:56); opt-in here
+  o->useTransform = 1;          // MultiLevelModelOptions.useTransform (:47)
   o->memoryBudgetBytes = 0;
   return DCSMC_OK;
 }
@@ -1235,6 +1327,8 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   chk("population staging (host)");
   if (e->dStage) cudaFree(e->dStage);
   chk("population staging (device)");
+  if (e->dSumm) cudaFree(e->dSumm);
+  if (e->dSumScratch) cudaFree(e->dSumScratch);
   void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dStepNodesTmp, e->dInj, e->dJavaState,
                   e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable};
   for (void* p : ptrs)
@@ -1289,6 +1383,8 @@ int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root, const int3
   e->children.assign(children, children + nEdges);
   e->parent = parent;
   e->height = height;
+  e->depth.assign(nNodes, 0);  // Node.level() (prototype/Node.java:72-75): root = 0
+  for (int k = 1; k < nNodes; ++k) e->depth[order[k]] = e->depth[parent[order[k]]] + 1;
   e->javaHash.clear();
   e->injHost.clear();
   for (double* p : e->injDev)
@@ -1362,7 +1458,7 @@ int32_t dcsmc_inject_uniforms(dcsmc_engine* e, int32_t node, const double* u, in
   if (!e) return DCSMC_EINVAL;
   if (node < 0 || node >= e->nNodes || e->model < 0) return e->fail(DCSMC_EINVAL, "bad node or no model");
   if (e->opt.rngMode != DCSMC_RNG_INJECTED) return e->fail(DCSMC_ESTATE, "engine was not created with DCSMC_RNG_INJECTED");
-  const int64_t need = (int64_t)e->opt.nParticles * slotsPerParticle(e, node) + e->opt.nParticles;
+  const int64_t need = (int64_t)e->opt.nParticles * slotsPerParticle(e, node) + e->opt.nParticles + summaryUniforms(e, node);
   if (!u || n < need) return e->fail(DCSMC_EINVAL, "node %d needs %lld uniforms, got %lld", node, (long long)need, (long long)n);
   if ((int)e->injHost.size() != e->nNodes) e->injHost.resize(e->nNodes);
   e->injHost[node].assign(u, u + need);
@@ -1406,6 +1502,28 @@ int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out) {
     return DCSMC_OK;
   }
   memcpy(out, e->hStats.data(), sizeof(dcsmc_node_stats_t) * e->nNodes);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_node_summary(dcsmc_engine* e, int32_t node, dcsmc_node_summary_t* out) {
+  if (!e || !out) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  memset(out, 0, sizeof *out);
+  if (e->opt.levelCutOffForOutput <= 0 || e->dSumm == nullptr) return DCSMC_OK;
+  if ((int)e->hStats.size() != e->nNodes || !e->hStats[node].done) return e->fail(DCSMC_ESTATE, "node %d not computed", node);
+  CK(cudaSetDevice(e->opt.device));
+  NodeSummary h;
+  CK(cudaMemcpyAsync(&h, e->dSumm + node, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  out->meanMean = h.meanMean;
+  out->meanSD = h.meanSD;
+  out->varMean = h.varMean;
+  out->varSD = h.varSD;
+  out->deltaMean = h.deltaMean;
+  out->deltaSD = h.deltaSD;
+  out->hasMean = (h.flags & 1) ? 1 : 0;
+  out->hasVar = (h.flags & 2) ? 1 : 0;
+  out->hasDelta = (h.flags & 4) ? 1 : 0;
   return DCSMC_OK;
 }
 

@@ -57,6 +57,9 @@ class DCOptions:
     maxBetaAttempts: int = 32
     retainPopulations: bool = False
     memoryBudgetBytes: int = 0
+    # impl-1 output options (prototype/smc/DivideConquerMCAlgorithm.java:47,56); 0 = no summaries
+    levelCutOffForOutput: int = 0
+    useTransform: bool = True
 
     def engine_kwargs(self, device: int = 0) -> Dict[str, Any]:
         return dict(
@@ -68,7 +71,8 @@ class DCOptions:
             maximumDistributionDepth=int(min(self.maximumDistributionDepth, 2 ** 31 - 1)),
             indexInCluster=self.indexInCluster, device=device, rngMode=self.rngMode,
             maxBetaAttempts=self.maxBetaAttempts, retainPopulations=1 if self.retainPopulations else 0,
-            memoryBudgetBytes=self.memoryBudgetBytes)
+            memoryBudgetBytes=self.memoryBudgetBytes, levelCutOffForOutput=int(self.levelCutOffForOutput),
+            useTransform=1 if self.useTransform else 0)
 
 
 class ParticlePopulation:
@@ -262,6 +266,49 @@ class DefaultProcessorFactory(DCProcessorFactory):
                 fh.write(str(self.rows[-1]["globalTime"] if self.rows else 0))
 
 
+class PosteriorSummaryProcessorFactory(DCProcessorFactory):
+    """impl-1's per-node output (printNodeStatistics / printDeltaNodeStatistics,
+    prototype/smc/DivideConquerMCAlgorithm.java:433-507) for nodes with level() < DCOptions.
+    levelCutOffForOutput: rows of `meanStats` (path, meanMean, meanSD), `varStats` (path, varMean,
+    varSD) and `deltaStats` (path of the child, deltaMean, deltaSD), computed on the device from the
+    resampled population (dcsmc_node_summary). The per-sample dump and the PDF histograms of the
+    reference are not produced."""
+
+    def __init__(self, resultsFolder: Optional[str] = None):
+        self.resultsFolder = resultsFolder
+        self.meanStats: List[Dict[str, Any]] = []
+        self.varStats: List[Dict[str, Any]] = []
+        self.deltaStats: List[Dict[str, Any]] = []
+
+    def build(self, context: DCProcessorFactoryContext) -> DCProcessor:
+        factory = self
+
+        class _P(DCProcessor):
+            def process(self, pop, children):
+                s = context.dc.nodeSummary(context.currentNode)
+                path = str(context.currentNode)
+                if s["hasMean"]:
+                    factory.meanStats.append(dict(path=path, meanMean=s["meanMean"], meanSD=s["meanSD"]))
+                if s["hasVar"]:
+                    factory.varStats.append(dict(path=path, varMean=s["varMean"], varSD=s["varSD"]))
+                if s["hasDelta"]:
+                    factory.deltaStats.append(dict(path=path, deltaMean=s["deltaMean"], deltaSD=s["deltaSD"]))
+
+        return _P()
+
+    def close(self):
+        if not self.resultsFolder:
+            return
+        os.makedirs(self.resultsFolder, exist_ok=True)
+        for name, rows, cols in (("meanStats", self.meanStats, ["path", "meanMean", "meanSD"]),
+                                 ("varStats", self.varStats, ["path", "varMean", "varSD"]),
+                                 ("deltaStats", self.deltaStats, ["path", "deltaMean", "deltaSD"])):
+            with open(os.path.join(self.resultsFolder, name + ".csv"), "w") as fh:
+                fh.write(",".join(cols) + "\n")
+                for r in rows:
+                    fh.write(",".join(str(r[c]) for c in cols) + "\n")
+
+
 # ---- orchestration ---------------------------------------------------------------------------------------
 
 class DistributedDC:
@@ -330,6 +377,7 @@ class DistributedDC:
         dist = self._dist()
         t0 = time.perf_counter()
         self._stats = None  # gathered lazily (a collective when sharded): see `stats`
+        self._summaries = None
         if dist is None:
             self.engine.run()
             info = self.engine.run_info()
@@ -562,6 +610,58 @@ class DistributedDC:
         out["resampled"] = mat[4].astype(np.int32)
         out["done"] = np.ones(self.csr.nNodes, np.int32)
         self._stats = out
+        return out
+
+    def nodeSummary(self, node) -> Dict[str, Any]:
+        """Posterior summaries of `node` (dcsmc_node_summary). Sharded runs: mean/var statistics live
+        on the node's owner, its delta statistics on the owner of its parent; the first call gathers
+        all of them (a collective every rank must make — start() does, through the processors)."""
+        i = self.csr.index[node] if not isinstance(node, (int, np.integer)) else int(node)
+        if self.options.levelCutOffForOutput <= 0:
+            return dict(hasMean=0, hasVar=0, hasDelta=0)
+        if getattr(self, "_summaries", None) is None:
+            self._summaries = self._gather_summaries()
+        return self._summaries.get(i, dict(hasMean=0, hasVar=0, hasDelta=0))
+
+    def _gather_summaries(self) -> Dict[int, Dict[str, Any]]:
+        csr, cut = self.csr, self.options.levelCutOffForOutput
+        depth = csr.depth()
+        nodes = [i for i in range(csr.nNodes) if depth[i] <= cut]  # delta rows sit one level below the cut
+        dist = self._dist()
+        keys = ["meanMean", "meanSD", "varMean", "varSD", "deltaMean", "deltaSD", "hasMean", "hasVar", "hasDelta"]
+        mat = np.zeros((len(nodes), len(keys)))
+        rank = dist.get_rank() if dist is not None else 0
+        own = self._nodeOwner if dist is not None else None
+        for r, i in enumerate(nodes):
+            mine = dist is None or own[i] == rank
+            parent = int(csr.parent[i])
+            parentMine = dist is None or (parent >= 0 and own[parent] == rank)
+            if not (mine or parentMine):
+                continue
+            try:
+                s = self.engine.node_summary(i)
+            except F.DcsmcError:
+                continue
+            if mine:
+                mat[r, 0:4] = [s.meanMean if s.hasMean else 0.0, s.meanSD if s.hasMean else 0.0,
+                               s.varMean if s.hasVar else 0.0, s.varSD if s.hasVar else 0.0]
+                mat[r, 6:8] = [s.hasMean, s.hasVar]
+            if parentMine and s.hasDelta:
+                mat[r, 4:6] = [s.deltaMean, s.deltaSD]
+                mat[r, 8] = 1
+        if dist is not None:
+            import torch
+
+            dev = torch.device("cuda", self.engine.options.device) if torch.cuda.is_available() else torch.device("cpu")
+            t = torch.from_numpy(mat).to(dev)
+            dist.all_reduce(t)
+            mat = t.cpu().numpy()
+        out = {}
+        for r, i in enumerate(nodes):
+            d = {k: float(mat[r, c]) for c, k in enumerate(keys)}
+            for k in ("hasMean", "hasVar", "hasDelta"):
+                d[k] = int(round(d[k]))
+            out[i] = d
         return out
 
     def _population_view(self, i: int, fetch=None) -> ParticlePopulation:

@@ -102,6 +102,11 @@ class Engine:
         self._ck(self._L.dcsmc_node_stats(self._h, node, C.byref(s)))
         return s
 
+    def node_summary(self, node: int) -> F.NodeSummary:
+        s = F.NodeSummary()
+        self._ck(self._L.dcsmc_node_summary(self._h, node, C.byref(s)))
+        return s
+
     def all_node_stats(self) -> Dict[str, np.ndarray]:
         arr = (F.NodeStats * self.nNodes)()
         self._ck(self._L.dcsmc_all_node_stats(self._h, arr))

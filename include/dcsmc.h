@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DCSMC_ABI_VERSION 1
+#define DCSMC_ABI_VERSION 2
 
 enum {
   DCSMC_OK = 0,
@@ -83,8 +83,13 @@ typedef struct dcsmc_options {
   int32_t maxBetaAttempts;   /* Beta rejection-sampler attempt cap; slot budget per leaf
                                 particle = 2*maxBetaAttempts uniforms (default 32) */
   int32_t retainPopulations; /* 1: keep every node's population resident (debug/parity) */
-  int32_t reserved0;
+  int32_t levelCutOffForOutput; /* DcSmcOptions.levelCutOffForOutput (prototype/smc/
+                                   DivideConquerMCAlgorithm.java:56): posterior summaries for nodes
+                                   with level() < this; 0 (default) = none, reference default 2 */
   int64_t memoryBudgetBytes; /* 0: use 85% of free device memory */
+  int32_t useTransform;      /* MultiLevelModelOptions.useTransform (:47): summaries on the
+                                logistic scale (default 1) */
+  int32_t reserved1;
 } dcsmc_options;
 
 typedef struct dcsmc_engine dcsmc_engine;
@@ -166,6 +171,26 @@ typedef struct dcsmc_node_stats_t {
 int32_t dcsmc_node_stats(const dcsmc_engine* e, int32_t node, dcsmc_node_stats_t* out);
 /* all nodes at once: out[nNodes] */
 int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out);
+
+/* Posterior summaries of impl-1 (printNodeStatistics / printDeltaNodeStatistics,
+ * DivideConquerMCAlgorithm.java:433-507), computed on the device right after the node step of every
+ * node with level() < levelCutOffForOutput, from the resampled population:
+ *   meanStats : mean / SD of inverseTransform(sampleValue) over the particles (:476-498)
+ *   varStats  : mean / SD of the particles' variance (internal nodes, :488-505)
+ *   deltaStats: for a node whose parent has level()+1 < levelCutOffForOutput, mean / SD of
+ *               inverseTransform(child sample) - inverseTransform(parent sample) with the child drawn
+ *               jointly (sampleChildrenJointly, :203-217) — reported under the CHILD's path (:460-463).
+ * Mean and SD follow commons-math3 DescriptiveStatistics (two-pass mean, bias-corrected variance).
+ * Gaussian draws: java.util.Random.nextGaussian's polar method on a separate slot-addressed uniform
+ * stream of the node. A node that was not resampled reports nothing (the reference's
+ * statistics assume equally weighted particles, :292). */
+typedef struct dcsmc_node_summary_t {
+  double meanMean, meanSD;
+  double varMean, varSD;
+  double deltaMean, deltaSD;
+  int32_t hasMean, hasVar, hasDelta, reserved;
+} dcsmc_node_summary_t;
+int32_t dcsmc_node_summary(dcsmc_engine* e, int32_t node, dcsmc_node_summary_t* out);
 
 /* DistributedDC.getRootPopulation() / ParticlePopulation accessors (DistributedDC.java:107;
  * SURVEY §8a row P): copies the node's population AFTER the node step (resampled if

@@ -217,6 +217,94 @@ static inline void brownian_calculate(int elemMode, double mean1, double var1, d
   *l = logl;
 }
 
+/* ------------------------------------------------------------------------------------
+ * impl-1 posterior summaries (DivideConquerMCAlgorithm.java:203-217, 433-507)
+ * ---------------------------------------------------------------------------------- */
+/* uniform pair `pair` of the node's summary stream */
+static void summary_pair(int64_t seed, int32_t nodeId, const double* injected, uint64_t pair,
+                         double* u0, double* u1) {
+  if (injected) {
+    *u0 = injected[2 * pair];
+    *u1 = injected[2 * pair + 1];
+    return;
+  }
+  uint32_t ctr[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)nodeId, 1u};
+  uint32_t key[2] = {(uint32_t)(uint64_t)seed, (uint32_t)((uint64_t)seed >> 32)};
+  uint32_t o[4];
+  orc_philox4x32_10(ctr, key, o);
+  *u0 = (double)(((uint64_t)(o[0] >> 6) << 27) | (uint64_t)(o[1] >> 5)) * 0x1.0p-53;
+  *u1 = (double)(((uint64_t)(o[2] >> 6) << 27) | (uint64_t)(o[3] >> 5)) * 0x1.0p-53;
+}
+
+/* java.util.Random.nextGaussian (JDK spec), without the cached second value */
+static double summary_gauss(int elemMode, int64_t seed, int32_t nodeId, const double* injected,
+                            uint64_t draw, int maxAtt) {
+  double v1 = 0.0, s = 0.5;
+  for (int a = 0; a < maxAtt; ++a) {
+    double u0, u1;
+    summary_pair(seed, nodeId, injected, draw * (uint64_t)maxAtt + (uint64_t)a, &u0, &u1);
+    v1 = 2 * u0 - 1;
+    const double v2 = 2 * u1 - 1;
+    s = v1 * v1 + v2 * v2;
+    if (s < 1 && s != 0) break;
+  }
+  const double multiplier = sqrt(-2 * orc_elem_log(elemMode, s) / s);
+  return v1 * multiplier;
+}
+
+static double summary_transform(int elemMode, int useTransform, double x) {
+  return useTransform ? 1.0 / (1.0 + orc_elem_exp(elemMode, -x)) : x; /* :610-616 */
+}
+
+/* commons-math3 DescriptiveStatistics.getMean / getStandardDeviation */
+static void descriptive(const double* x, int n, double* mean, double* sd) {
+  double sum = 0;
+  for (int i = 0; i < n; ++i) sum += x[i];
+  const double xbar = sum / n;
+  double corr = 0;
+  for (int i = 0; i < n; ++i) corr += x[i] - xbar;
+  const double m = xbar + corr / n;
+  double accum = 0, accum2 = 0;
+  for (int i = 0; i < n; ++i) {
+    const double dev = x[i] - m;
+    accum += dev * dev;
+    accum2 += dev;
+  }
+  *mean = m;
+  *sd = n > 1 ? sqrt((accum - (accum2 * accum2 / n)) / (n - 1.0)) : 0.0;
+}
+
+int orc_node_summaries(int elemMode, int64_t seed, int32_t nodeId, int32_t N, int32_t maxAtt,
+                       int32_t useTransform, const double* injected, const double* mean,
+                       const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
+                       const double* childMean, const double* childVar, double* out) {
+  double* buf = (double*)malloc(sizeof(double) * (size_t)N);
+  if (!buf) return 1;
+  const uint64_t G = 2 + (uint64_t)C;
+  /* printNodeStatistics :476-498 */
+  for (int i = 0; i < N; ++i) {
+    const double natural = summary_gauss(elemMode, seed, nodeId, injected, (uint64_t)i * G, maxAtt) * sqrt(msgVar[i]) + mean[i];
+    buf[i] = summary_transform(elemMode, useTransform, natural);
+  }
+  descriptive(buf, N, &out[0], &out[1]);
+  out[2] = out[3] = 0.0;
+  if (variance) descriptive(variance, N, &out[2], &out[3]);
+  /* printDeltaNodeStatistics :433-469 with sampleChildrenJointly :203-217 */
+  for (int c = 0; doDelta && c < C; ++c) {
+    for (int i = 0; i < N; ++i) {
+      const double root = summary_gauss(elemMode, seed, nodeId, injected, (uint64_t)i * G + 1, maxAtt) * sqrt(msgVar[i]) + mean[i];
+      double um, us, ul;
+      brownian_calculate(elemMode, mean[i], msgVar[i], 0.0, childMean[(size_t)c * N + i], childVar[(size_t)c * N + i], 0.0,
+                         variance ? variance[i] : NAN, 0.0, &um, &us, &ul);
+      const double child = summary_gauss(elemMode, seed, nodeId, injected, (uint64_t)i * G + 2 + c, maxAtt) * sqrt(us) + um;
+      buf[i] = summary_transform(elemMode, useTransform, child) - summary_transform(elemMode, useTransform, root);
+    }
+    descriptive(buf, N, &out[4 + 2 * c], &out[5 + 2 * c]);
+  }
+  free(buf);
+  return 0;
+}
+
 /* combine(List children, double variance), :18-41 */
 void orc_brownian_combine(int elemMode, int C, const double* mean, const double* var,
                           const double* ll, double variance, double* out3) {

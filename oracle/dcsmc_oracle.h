@@ -107,6 +107,21 @@ double orc_elem_exp(int mode, double x);
  * in: mean[C], var[C], ll[C]; out: 3 doubles */
 void orc_brownian_combine(int elemMode, int C, const double* mean, const double* var,
                           const double* ll, double variance, double* out3);
+/* impl-1 posterior summaries of ONE node (printNodeStatistics / printDeltaNodeStatistics /
+ * sampleChildrenJointly, prototype/smc/DivideConquerMCAlgorithm.java:203-217,433-507) from its
+ * RESAMPLED population: mean[N], msgVar[N], variance[N] (NULL for a leaf) and, for the deltas, the
+ * children's messages aligned with the parent's particles, childMean/childVar [C][N].
+ * Gaussian draws: java.util.Random.nextGaussian's polar method; attempt a of draw d uses the uniform
+ * pair d*maxAtt + a of the node's summary stream — Philox counter word 3 = 1, or `injected`
+ * (2 uniforms per pair) when not NULL. Draws per particle: 2 + C (0: node statistics, 1: joint root,
+ * 2+c: child c). Mean / SD as commons-math3 DescriptiveStatistics (two-pass mean, bias-corrected SD).
+ * out: meanMean, meanSD, varMean, varSD, then (deltaMean, deltaSD) per child.
+ * PARITY UNPINNED: the reference holds no fixture for these; Normal.generate and logistic are
+ * un-vendored bayonet code restated from recall (mean + sqrt(var)*nextGaussian; 1/(1+exp(-x))). */
+int orc_node_summaries(int elemMode, int64_t seed, int32_t nodeId, int32_t N, int32_t maxAtt,
+                       int32_t useTransform, const double* injected, const double* mean,
+                       const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
+                       const double* childMean, const double* childVar, double* out);
 int32_t orc_slots_per_particle(const orc_options* opt, const orc_tree* tree, int32_t node);
 
 #ifdef __cplusplus

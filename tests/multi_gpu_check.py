@@ -50,6 +50,31 @@ def main():
                 assert tot.item() > 0, "nothing crossed NVLink"
                 transport = ddc._transportChoice
                 ddc.close()
+    # posterior summaries (levelCutOffForOutput): mean/var statistics come from the node's owner, delta
+    # statistics from the owner of its parent, which reads the children over NVLink
+    opt = d.DCOptions(nParticles=N, maximumDistributionDepth=2, levelCutOffForOutput=2)
+    ddc = d.DistributedDC.createInstance(opt, d.MultiLevelProposalFactory(dataset=ds), ds.getTree(), device=local)
+    ddc.start()
+    csr = ds.getTree().to_csr()
+    got = {i: ddc.nodeSummary(i) for i in range(csr.nNodes)}
+    ddc.engine.run()
+    depth = csr.depth()
+    nDelta = 0
+    for i in range(csr.nNodes):
+        s1 = ddc.engine.node_summary(i)
+        if depth[i] > 2:
+            continue
+        g = got[i]
+        assert (g["hasMean"], g["hasVar"], g["hasDelta"]) == (s1.hasMean, s1.hasVar, s1.hasDelta), (i, g)
+        if g["hasMean"]:
+            assert g["meanMean"] == s1.meanMean and g["meanSD"] == s1.meanSD, (i, g)
+        if g["hasVar"]:
+            assert g["varMean"] == s1.varMean and g["varSD"] == s1.varSD, (i, g)
+        if g["hasDelta"]:
+            assert g["deltaMean"] == s1.deltaMean and g["deltaSD"] == s1.deltaSD, (i, g)
+            nDelta += 1
+    assert nDelta >= 2
+    ddc.close()
     # the reference's own example model (Doc.java:162-237) through the same sharded path
     from test_gpu_dc_api import transition, prior
 

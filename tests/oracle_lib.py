@@ -116,6 +116,10 @@ def lib():
         L.orc_elem_exp.argtypes = [C.c_int, C.c_double]
         L.orc_brownian_combine.restype = None
         L.orc_brownian_combine.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
+        dp = C.POINTER(C.c_double)
+        L.orc_node_summaries.restype = C.c_int
+        L.orc_node_summaries.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp,
+                                         C.c_int32, C.c_int32, dp, dp, dp]
         L.orc_slots_per_particle.restype = C.c_int32
         L.orc_slots_per_particle.argtypes = [C.POINTER(OrcOptions), C.POINTER(OrcTree), C.c_int32]
         _lib = L
@@ -235,3 +239,39 @@ def slots_per_particle(csr, node: int, *, model=MODEL_MULTILEVEL, maxBetaAttempt
     if leafKind is not None and leafKind[node] == LEAF_GAUSS_OBS:
         return 0
     return 2 * maxBetaAttempts
+
+
+def node_summaries(ref: OracleResult, csr, node: int, *, levelCutOffForOutput: int, masterRandomSeed: int = 31,
+                   maxBetaAttempts: int = 32, useTransform: bool = True, elemMode: int = ELEM_FDLIBM,
+                   injected: Optional[np.ndarray] = None) -> Dict[str, object]:
+    """impl-1 posterior summaries of `node` from a dumped oracle run (ref = run(..., dump=True)): the
+    resampled population is rebuilt from the pre-resampling particles and the ancestor indices, the
+    children's messages are aligned with it, and orc_node_summaries restates the reference's loops."""
+    L = lib()
+    N = ref.state.shape[2]
+    depth = csr.depth()
+    C_ = csr.nChildren(node)
+    kids = [int(c) for c in csr.children[csr.childOffsets[node]:csr.childOffsets[node + 1]]]
+    a = ref.anc[node]  # identity when the node was not resampled
+    mean = np.ascontiguousarray(ref.state[node][0][a])
+    msgVar = np.ascontiguousarray(ref.state[node][1][a])
+    variance = np.ascontiguousarray(ref.state[node][5][a]) if C_ > 0 else None
+    doDelta = 1 if (depth[node] + 1 < levelCutOffForOutput and C_ > 0) else 0
+    cm = np.zeros((max(C_, 1), N))
+    cv = np.zeros((max(C_, 1), N))
+    for k, ch in enumerate(kids):
+        ci = ref.anc[ch][a]
+        cm[k] = ref.state[ch][0][ci]
+        cv[k] = ref.state[ch][1][ci]
+    out = np.zeros(4 + 2 * max(C_, 1))
+    inj = None if injected is None else np.ascontiguousarray(injected, dtype=np.float64)
+    rc = L.orc_node_summaries(elemMode, masterRandomSeed, node, N, maxBetaAttempts, 1 if useTransform else 0,
+                              _p(inj, C.c_double), _p(mean, C.c_double), _p(msgVar, C.c_double),
+                              _p(variance, C.c_double), C_, doDelta, _p(cm, C.c_double), _p(cv, C.c_double),
+                              _p(out, C.c_double))
+    assert rc == 0
+    res = dict(meanMean=out[0], meanSD=out[1], hasVar=C_ > 0, varMean=out[2], varSD=out[3], delta={})
+    if doDelta:
+        for k, ch in enumerate(kids):
+            res["delta"][ch] = (out[4 + 2 * k], out[5 + 2 * k])
+    return res

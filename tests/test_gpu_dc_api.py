@@ -158,7 +158,7 @@ def test_native_cli_run_matches_engine(tmp_path):
     res = tmp_path / "results" / "latest"
     r = subprocess.run([cli, "-dataFile", str(path), "-nParticles", "5000", "-resamplingScheme", "STRATIFIED",
                         "-dc.masterRandomSeed", "31", "-nThreadsPerNode", "4", "-maximumDistributionDepth", "2",
-                        "-resultsFolder", str(res)], capture_output=True, text=True)
+                        "-levelCutOffForOutput", "2", "-resultsFolder", str(res)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     ds = d.MultiLevelDataset(str(path))
     csr = ds.getTree().to_csr()
@@ -171,3 +171,67 @@ def test_native_cli_run_matches_engine(tmp_path):
     last = lines[-1].split(",")
     assert last[0] == csr.nodes[0].toString() and float(last[1]) == ref.ess[0] and float(last[3]) == ref.logNormEstimate[0]
     assert "timing: node=" in r.stdout and "logZ estimate" in r.stdout
+    # impl-1 summaries through the CLI equal the oracle's restatement
+    ref_d = o.run(csr, 5000, resamplingScheme=o.STRATIFIED, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                  elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+    want = o.node_summaries(ref_d, csr, 0, levelCutOffForOutput=2)
+    rows_m = [l.split(",") for l in open(res / "meanStats.csv").read().strip().splitlines()[1:]]
+    root = [r_ for r_ in rows_m if r_[0] == csr.nodes[0].toString()][0]
+    assert abs(float(root[1]) - want["meanMean"]) < 1e-12 and abs(float(root[2]) - want["meanSD"]) < 1e-12
+    nDelta = len(open(res / "deltaStats.csv").read().strip().splitlines()) - 1
+    assert nDelta == csr.nChildren(0)
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_posterior_summaries_match_oracle(scheme, tmp_path):
+    """impl-1's meanStats / varStats / deltaStats (DivideConquerMCAlgorithm.java:433-507)
+    for nodes with level() < levelCutOffForOutput, computed on the device right after the node step.
+    Samples are bit-identical by construction (same uniforms, fdlibm log/exp, IEEE sqrt); the statistics
+    are fp64 sums in a different (fixed) order, compared at 1e-12 relative (north star: 1e-9)."""
+    rows = synth.small_multilevel_rows(seed=11)
+    ds = d.MultiLevelDataset(rows=rows)
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    N, cut = 6000, 2
+    ref = o.run(csr, N, masterRandomSeed=31, resamplingScheme=scheme, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+    opt = d.DCOptions(nParticles=N, resamplingScheme=d.ResamplingScheme(scheme), levelCutOffForOutput=cut)
+    ddc = d.DistributedDC.createInstance(opt, d.MultiLevelProposalFactory(dataset=ds), ds.getTree(), device=0)
+    summ = d.PosteriorSummaryProcessorFactory(resultsFolder=str(tmp_path / "results"))
+    ddc.addProcessorFactory(summ)
+    ddc.start()
+    assert np.array_equal(ddc.stats["logNormEstimate"], ref.logNormEstimate)  # summaries do not disturb the run
+    depth = csr.depth()
+    close = lambda x, y: abs(x - y) <= 1e-12 * max(1.0, abs(y))
+    nMean = nVar = nDelta = 0
+    for i in range(csr.nNodes):
+        s = ddc.engine.node_summary(i)
+        if depth[i] >= cut:
+            assert not s.hasMean and not s.hasVar
+            continue
+        want = o.node_summaries(ref, csr, i, levelCutOffForOutput=cut)
+        assert s.hasMean and close(s.meanMean, want["meanMean"]) and close(s.meanSD, want["meanSD"]), (i, s.meanMean, want)
+        nMean += 1
+        assert bool(s.hasVar) == want["hasVar"]
+        if want["hasVar"]:
+            assert close(s.varMean, want["varMean"]) and close(s.varSD, want["varSD"])
+            nVar += 1
+        for ch, (dm, dsd) in want["delta"].items():
+            c = ddc.engine.node_summary(ch)
+            assert c.hasDelta and close(c.deltaMean, dm) and close(c.deltaSD, dsd), (i, ch, c.deltaMean, dm)
+            nDelta += 1
+    assert nMean >= 3 and nVar >= 1 and nDelta >= 2
+    assert 0.0 < ddc.engine.node_summary(0).meanMean < 1.0  # logistic scale
+    # the processor wrote the reference's three tables
+    for name, n in (("meanStats", nMean), ("varStats", nVar), ("deltaStats", nDelta)):
+        lines = open(tmp_path / "results" / (name + ".csv")).read().strip().splitlines()
+        assert len(lines) == n + 1, (name, len(lines), n)
+    ddc.close()
+    # off by default: no summaries, same run
+    from dcsmc_b200.engine import Engine
+
+    with Engine(nParticles=N, resamplingScheme=scheme) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        assert not e.node_summary(0).hasMean

@@ -22,7 +22,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/dcsmc.h but not exported"
     assert declared == set(_ffi.SYMBOLS)
-    assert L.dcsmc_abi_version() == 1
+    assert L.dcsmc_abi_version() == 2
 
 
 def test_options_default_mirror_dcoptions():
