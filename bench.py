@@ -231,6 +231,7 @@ def run_ours(args):
     # every step re-uploads the topology + model from host arrays (set_tree / set_*_model) and reads
     # the per-node statistics and the root population back to the host.
     h2d = d2h = 0
+    host_out = (np.empty((6, N)), None, np.empty(N))
 
     def e2e_step():
         nonlocal h2d, d2h
@@ -241,7 +242,7 @@ def run_ours(args):
         h2d = ddc.lastRun["h2dBytes"]
         d2h = ddc.lastRun["d2hBytes"]
         if rank == ddc.rootOwner:
-            rs, _, rw = ddc.engine.population(0)
+            rs, _, rw = ddc.engine.population(0, out=host_out)  # the caller's own host buffers, reused
             d2h += rs.nbytes + rw.nbytes
         return stats
 

@@ -105,6 +105,7 @@ struct dcsmc_engine {
   uint64_t* dJavaState = nullptr;
   double *dMarkovT = nullptr, *dMarkovPrior = nullptr;
   bool tablesDirty = true;
+  size_t tableNodesCap = 0, tableEdgesCap = 0;  // sizes the device tables were allocated for
 
   // population pool
   char* pool = nullptr;
@@ -383,7 +384,11 @@ int uploadTables(dcsmc_engine* e) {
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
   if (e->model < 0) return e->fail(DCSMC_ESTATE, "no proposal model set (dcsmc_set_*_model)");
   const int nN = e->nNodes;
+  // tables are re-allocated only when the tree grows: cudaFree/cudaMalloc synchronise the device, and
+  // a caller that re-sends the same topology every step (bench.py's end-to-end leg) pays them each time
+  const bool keep = e->dNodes != nullptr && (size_t)nN <= e->tableNodesCap && e->children.size() <= e->tableEdgesCap;
   auto re = [&](void** p, size_t bytes) -> cudaError_t {
+    if (keep && *p) return cudaSuccess;
     if (*p) cudaFree(*p);
     *p = nullptr;
     return cudaMalloc(p, bytes ? bytes : 8);
@@ -398,6 +403,10 @@ int uploadTables(dcsmc_engine* e) {
   CK(re((void**)&e->dChildren, sizeof(int32_t) * std::max<size_t>(1, e->children.size())));
   CK(re((void**)&e->dInj, sizeof(double*) * nN));
   CK(re((void**)&e->dJavaState, sizeof(uint64_t) * nN));
+  if (!keep) {
+    e->tableNodesCap = (size_t)nN;
+    e->tableEdgesCap = e->children.size();
+  }
   CK(cudaMemcpyAsync(e->dChildren, e->children.data(), sizeof(int32_t) * e->children.size(),
                      cudaMemcpyHostToDevice, e->stream));
   e->pendingH2D += (int64_t)(sizeof(int32_t) * e->children.size() + (sizeof(LeafConst) + sizeof(uint64_t)) * nN);
@@ -412,8 +421,13 @@ int uploadTables(dcsmc_engine* e) {
     js[n] = java_scramble(java_node_seed(e->opt.masterRandomSeed, e->javaHash.empty() ? 0 : e->javaHash[n]));
   CK(cudaMemcpyAsync(e->dJavaState, js.data(), sizeof(uint64_t) * nN, cudaMemcpyHostToDevice, e->stream));
   if (e->model == DCSMC_MODEL_MARKOV) {
-    CK(re((void**)&e->dMarkovT, sizeof(double) * e->markovT.size()));
-    CK(re((void**)&e->dMarkovPrior, sizeof(double) * e->markovPrior.size()));
+    auto reAlways = [&](void** p, size_t bytes) -> cudaError_t {  // sized by nStates, not by the tree
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+      return cudaMalloc(p, bytes ? bytes : 8);
+    };
+    CK(reAlways((void**)&e->dMarkovT, sizeof(double) * e->markovT.size()));
+    CK(reAlways((void**)&e->dMarkovPrior, sizeof(double) * e->markovPrior.size()));
     CK(cudaMemcpyAsync(e->dMarkovT, e->markovT.data(), sizeof(double) * e->markovT.size(),
                        cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->dMarkovPrior, e->markovPrior.data(), sizeof(double) * e->markovPrior.size(),

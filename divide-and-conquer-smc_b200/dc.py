@@ -148,8 +148,12 @@ class MultiLevelProposalFactory(DCProposalFactory):
         return self._dataset
 
     def configure(self, engine: Engine, csr: CsrTree):
-        nT, nS = self.getDataset().leaf_arrays(csr)
-        engine.set_multilevel_model(nT, nS, None, None, self.variancePrior)
+        # the per-node (nTrials, nSuccesses) arrays are a pure function of (dataset, numbering): built once
+        cached = getattr(self, "_leafArrays", None)
+        if cached is None or cached[0] is not csr:
+            nT, nS = self.getDataset().leaf_arrays(csr)
+            self._leafArrays = cached = (csr, nT, nS)
+        engine.set_multilevel_model(cached[1], cached[2], None, None, self.variancePrior)
 
 
 class GaussianLeafProposalFactory(DCProposalFactory):
@@ -161,13 +165,16 @@ class GaussianLeafProposalFactory(DCProposalFactory):
         self.variancePrior = variancePrior
 
     def configure(self, engine: Engine, csr: CsrTree):
-        obs = np.zeros(csr.nNodes)
-        kind = np.zeros(csr.nNodes, np.int32)
-        for i, n in enumerate(csr.nodes):
-            if csr.nChildren(i) == 0:
-                obs[i] = self.leafObs[n]
-                kind[i] = F.LEAF_GAUSS_OBS
-        engine.set_multilevel_model(None, None, kind, obs, self.variancePrior)
+        cached = getattr(self, "_leafArrays", None)
+        if cached is None or cached[0] is not csr:
+            obs = np.zeros(csr.nNodes)
+            kind = np.zeros(csr.nNodes, np.int32)
+            for i, n in enumerate(csr.nodes):
+                if csr.nChildren(i) == 0:
+                    obs[i] = self.leafObs[n]
+                    kind[i] = F.LEAF_GAUSS_OBS
+            self._leafArrays = cached = (csr, kind, obs)
+        engine.set_multilevel_model(None, None, cached[1], cached[2], self.variancePrior)
 
 
 class MarkovChainNaiveProposalFactory(DCProposalFactory):

@@ -115,11 +115,19 @@ class Engine:
             ("resampled", "i4"), ("done", "i4")]))
         return {k: raw[k].copy() for k in raw.dtype.names}
 
-    def population(self, node: int, state=True, istate=False, weights=True):
+    def population(self, node: int, state=True, istate=False, weights=True, out=None):
+        """Copy of the node's population after its node step. `out` = (state[6][N] f64, istate[N] i32,
+        weights[N] f64) lets a caller reuse its host buffers (any entry may be None)."""
         N = self.N
-        st = np.empty((6, N)) if state else None
-        ist = np.empty(N, np.int32) if istate else None
-        w = np.empty(N) if weights else None
+        if out is not None:
+            st, ist, w = out
+            for a, shape, dt in ((st, (6, N), np.float64), (ist, (N,), np.int32), (w, (N,), np.float64)):
+                if a is not None and (a.shape != shape or a.dtype != dt or not a.flags["C_CONTIGUOUS"]):
+                    raise ValueError(f"population(out=...): expected C-contiguous {shape} {dt}")
+        else:
+            st = np.empty((6, N)) if state else None
+            ist = np.empty(N, np.int32) if istate else None
+            w = np.empty(N) if weights else None
         self._ck(self._L.dcsmc_population_copy_to_host(
             self._h, node, _ptr(st, C.c_double), _ptr(ist, C.c_int32), _ptr(w, C.c_double)))
         return st, ist, w

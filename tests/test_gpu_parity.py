@@ -41,7 +41,7 @@ def compare_all(e, ref, csr, markov=False):
             assert np.array_equal(state, ref.state[n], equal_nan=True), f"state node {n}"
 
 
-@pytest.mark.parametrize("N", [1, 33, 1000, 5000, 20000])  # <= 16384: shared-memory node kernel; above: generic path
+@pytest.mark.parametrize("N", [1, 33, 1000, 5000, 20000, 20001, 150001])  # <= 16384: shared-memory node kernel; above: generic path (odd N: dart pairs straddle the region start)
 @pytest.mark.parametrize("threshold", [1.0 + 1e-10, 0.5])
 @pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
 def test_multilevel_philox_bit_exact(N, threshold, scheme):
