@@ -895,6 +895,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.nStates = e->nStates;
   c.javaStepsInternal = e->model == DCSMC_MODEL_MARKOV ? 1 : 2;
   c.seed = (uint64_t)e->opt.masterRandomSeed;
+  c.rk = philox_round_keys(c.seed);
   c.inj = e->dInj;
   c.javaState = e->dJavaState;
   c.markovT = e->dMarkovT;
