@@ -152,6 +152,7 @@ struct dcsmc_engine {
   int invB = 1;
   size_t leafSmemSet[3] = {0, 0, 0};
   size_t smallSmemSet[3] = {0, 0, 0};
+  size_t smallSmemSet512[3] = {0, 0, 0};
   std::vector<CachedPlan> planCache;
   const CachedPlan* devicePlan = nullptr;  // whose descriptors are currently uploaded
   std::vector<int> descDirty;              // nodes whose device descriptor was rewritten since then
@@ -812,13 +813,21 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
   if (smallNode) {
     // the population fits in shared memory: one block per node does everything after propose
     const size_t smem = smalln_smem_bytes(c.Npad);
-    if (smem > e->smallSmemSet[RNG]) {
-      CK(cudaFuncSetAttribute(k_node_small<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      e->smallSmemSet[RNG] = smem;
+    const bool wide = smalln_threads(c.Npad) == 1024;
+    size_t& smemSet = wide ? e->smallSmemSet[RNG] : e->smallSmemSet512[RNG];
+    if (smem > smemSet) {
+      if (wide)
+        CK(cudaFuncSetAttribute(k_node_small<RNG, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else
+        CK(cudaFuncSetAttribute(k_node_small<RNG, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smemSet = smem;
     }
     {
       ProfScope p(e, DCSMC_K_SCAN, sR);
-      k_node_small<RNG><<<st.count, SMALLN_THREADS, smem, sR>>>(c);
+      if (wide)
+        k_node_small<RNG, 1024><<<st.count, 1024, smem, sR>>>(c);
+      else
+        k_node_small<RNG, 512><<<st.count, 512, smem, sR>>>(c);
     }
     CK(cudaGetLastError());
     return launchSummaries<RNG>(e, c, st, sR);
