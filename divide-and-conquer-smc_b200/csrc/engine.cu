@@ -801,8 +801,15 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
       ProfScope p(e, DCSMC_K_INTERNAL, sP);
       k_internal_prelude<<<(st.count + 3) / 4, 128, 0, sP>>>(c);
     }
+    // can the linear-space product of the children's weights underflow anywhere in this step?
+    int maxC = 0;
+    for (int k = 0; k < st.count; ++k) maxC = std::max(maxC, nChildrenOf(e, e->planStepNodes[st.offset + k]));
+    const bool wide = (double)maxC * std::log10((double)N) > 300.0;
     ProfScope p(e, DCSMC_K_INTERNAL, sP);
-    k_internal_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+    if (wide)
+      k_internal_propose<RNG, true><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+    else
+      k_internal_propose<RNG, false><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
   }
   if (sR != sP) {  // the chain of this chunk starts when its propose kernel is done
     cudaEvent_t ev = nextEvent(e);

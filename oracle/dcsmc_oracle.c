@@ -575,7 +575,16 @@ static population* node_step(orc_ctx* ctx, int32_t node, population** kids, int 
       lw = propose_gauss_leaf(ctx->tree->leafObs[node], &parts[i]);
     else
       lw = propose_internal(ctx, &rng, kids, C, i, mean, var, ll, &parts[i]);
-    logW[i] = impl1 ? lw : LOG(childrenWeightProduct) + lw;
+    double logProduct = LOG(childrenWeightProduct); /* DCRecursion.java:63 */
+    if (!impl1 && C > 0 && childrenWeightProduct == 0.0) {
+      /* EXTENSION (DESIGN.md "Known deviations"): the linear-space product underflowed to 0 — with
+       * resampled children that is N^-C < 4.9e-324, e.g. 54 children at N = 1e6 — and the reference
+       * returns log(0) = -inf for every particle here. The engine evaluates sum_c log W_c instead
+       * (left to right); a particle with a genuinely zero child weight still gets -inf. */
+      logProduct = 0.0;
+      for (int c = 0; c < C; ++c) logProduct += LOG(kids[c]->w ? kids[c]->w[i] : 1.0 / (double)N);
+    }
+    logW[i] = impl1 ? lw : logProduct + lw;
   }
   free(mean);
 

@@ -240,3 +240,30 @@ def test_gpu_reproduces_the_reference_recorded_run_to_every_digit():
         names = [n.toString() for n in csr.nodes]
         st = e.all_node_stats()
         assert sorted(names[i] for i in np.nonzero(st["resampled"])[0]) == ["0-0", "0-1"]
+
+
+@pytest.mark.parametrize("threshold", [1.0 + 1e-10, 0.5])
+def test_wide_node_weight_product_underflow(threshold):
+    """The reference multiplies the children's weights in linear space (DCRecursion.java:55-63); with C
+    children that is N^-C, which underflows to 0 for C*log10(N) > 323 (54 children at nParticles = 1e6,
+    BASELINE config 3) and makes every log weight -inf. Engine and oracle fall back to the sum of logs
+    exactly there (documented deviation): logZ stays finite, and both still agree bit for bit.
+    threshold > 1: children resampled (per-node constant); 0.5: leaves arrive weighted (per particle)."""
+    N, C = 2000, 110  # 2000^-110 = 1e-363
+    rows = [["NY", "c0", "d0", f"s{k}", "2006", str(40 + (7 * k) % 50), str(10 + (3 * k) % 25)] for k in range(C)]
+    ds = d.MultiLevelDataset(rows=rows)
+    tree = ds.getTree()
+    csr = tree.to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    wide = [i for i in range(csr.nNodes) if csr.nChildren(i) >= C]
+    assert wide, "fixture must contain a node with >= 110 children"
+    assert (1.0 / N) ** C == 0.0
+    ref = o.run(csr, N, masterRandomSeed=31, resamplingScheme=o.STRATIFIED, relativeEssThreshold=threshold,
+                rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+    assert np.all(np.isfinite(ref.logNormEstimate))
+    with Engine(nParticles=N, masterRandomSeed=31, resamplingScheme=o.STRATIFIED, relativeEssThreshold=threshold,
+                retainPopulations=1) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        compare_all(e, ref, csr)
