@@ -152,3 +152,128 @@ def test_fdlibm_elementary_functions_within_one_ulp_of_libm():
     assert L.orc_elem_exp(o.ELEM_FDLIBM, -math.inf) == 0.0
     assert L.orc_elem_exp(o.ELEM_FDLIBM, -800.0) == 0.0
     assert L.orc_elem_log(o.ELEM_FDLIBM, 5e-324) == math.log(5e-324)
+
+
+# ---- committed fixtures (tests/golden/, generated by tests/golden/make_golden.py) ---------------------------
+import hashlib
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name + ".json")) as fh:
+        return json.load(fh)
+
+
+def _unhex(xs):
+    return np.array([float.fromhex(x) for x in xs])
+
+
+def _digest(a):
+    a = np.asarray(a)
+    if a.dtype.kind == "f":
+        a = np.where(np.isnan(a), np.nan, a)  # one NaN bit pattern (leaves carry variance = NaN)
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_doc_recorded_run_fixture_is_what_the_tests_pin():
+    g = _load("doc_recorded_run")
+    assert float(g["root"]["logZ"]) == -3.5950250310183574 and float(g["root"]["ESS"]) == 548622.6672945316
+    assert float(g["root"]["rESS"]) == 0.5486226672945316
+    assert float(g["exactLogZ"]) == pytest.approx(exact_log_z(3), rel=1e-14)
+    csr = d.perfectBinaryTree(3).to_csr()
+    r = o.run(csr, g["nParticles"], model=o.MODEL_MARKOV, masterRandomSeed=g["masterRandomSeed"],
+              resamplingScheme=o.MULTINOMIAL, relativeEssThreshold=g["relativeEssThreshold"], rngMode=o.RNG_JAVA,
+              sumMode=o.SUM_JAVA, elemMode=o.ELEM_LIBM, transition=np.array(g["transition"]), prior=np.array(g["prior"]))
+    assert repr(float(r.logNormEstimate[0])) == g["root"]["logZ"]
+    assert repr(float(r.ess[0])) == g["root"]["ESS"]
+    assert repr(float(r.relEss[0])) == g["root"]["rESS"]
+
+
+def test_oracle_reproduces_committed_multilevel_fixture():
+    """Guards the oracle itself: any change to the restatement that moves a bit of the small seeded run
+    (statistics, log weights, ancestors, states, root population) fails here, on CPU."""
+    from dcsmc_b200 import synth
+
+    g = _load("multilevel_small")
+    ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows())
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    assert [int(x) for x in csr.childOffsets] == g["childOffsets"] and [int(x) for x in csr.children] == g["children"]
+    assert [int(x) for x in nT] == g["nTrials"] and [int(x) for x in nS] == g["nSuccesses"]
+    for case in g["cases"]:
+        r = o.run(csr, g["nParticles"], masterRandomSeed=g["masterRandomSeed"], resamplingScheme=case["resamplingScheme"],
+                  relativeEssThreshold=float.fromhex(case["relativeEssThreshold"]), rngMode=o.RNG_PHILOX,
+                  sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+        assert np.array_equal(r.logNormEstimate, _unhex(case["logNormEstimate"]))
+        assert np.array_equal(r.ess, _unhex(case["ess"]))
+        assert np.array_equal(r.logScaling, _unhex(case["logScaling"]))
+        assert [int(x) for x in r.resampled] == case["resampled"]
+        for n in range(csr.nNodes):
+            assert _digest(r.anc[n].astype(np.int32)) == case["ancestors_sha256"][n], n
+            assert _digest(r.logw[n]) == case["logw_sha256"][n], n
+            assert _digest(r.state[n]) == case["state_sha256"][n], n
+        assert _digest(r.rootState) == case["rootState_sha256"] and _digest(r.rootWeights) == case["rootWeights_sha256"]
+
+
+def test_oracle_reproduces_committed_summary_and_underflow_fixtures():
+    from dcsmc_b200 import synth
+
+    g = _load("summaries_small")
+    ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows(seed=11))
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    for case in g["cases"]:
+        r = o.run(csr, g["nParticles"], masterRandomSeed=31, resamplingScheme=case["resamplingScheme"], rngMode=o.RNG_PHILOX,
+                  sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+        for i, want in case["nodes"].items():
+            s = o.node_summaries(r, csr, int(i), levelCutOffForOutput=g["levelCutOffForOutput"])
+            assert s["meanMean"] == float.fromhex(want["meanMean"]) and s["meanSD"] == float.fromhex(want["meanSD"])
+            assert bool(s["hasVar"]) == want["hasVar"]
+            assert s["varMean"] == float.fromhex(want["varMean"]) and s["varSD"] == float.fromhex(want["varSD"])
+            assert {str(c): [float(a).hex(), float(b).hex()] for c, (a, b) in s["delta"].items()} == want["delta"]
+    # summaries are statistically sane: on the logistic scale the root mean is a success probability
+    root = g["cases"][0]["nodes"]["0"]
+    assert 0.0 < float.fromhex(root["meanMean"]) < 1.0 and float.fromhex(root["meanSD"]) > 0.0
+    g = _load("wide_underflow")
+    N, C_ = g["nParticles"], g["nChildren"]
+    rows = [["NY", "c0", "d0", f"s{k}", "2006", str(40 + (7 * k) % 50), str(10 + (3 * k) % 25)] for k in range(C_)]
+    ds = d.MultiLevelDataset(rows=rows)
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    assert (1.0 / N) ** C_ == 0.0  # the reference's linear-space product underflows here
+    for case in g["cases"]:
+        r = o.run(csr, N, masterRandomSeed=31, resamplingScheme=g["resamplingScheme"],
+                  relativeEssThreshold=float.fromhex(case["relativeEssThreshold"]), rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                  elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
+        assert np.all(np.isfinite(r.logNormEstimate))
+        assert np.array_equal(r.logNormEstimate, _unhex(case["logNormEstimate"])) and np.array_equal(r.ess, _unhex(case["ess"]))
+    # the fallback is consistent with a run that does not underflow: same model at N = 100 (100^-110 = 1e-220)
+    small = o.run(csr, 100, masterRandomSeed=31, resamplingScheme=g["resamplingScheme"], rngMode=o.RNG_PHILOX,
+                  sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
+    big = _unhex(g["cases"][0]["logNormEstimate"])[0]
+    assert abs(small.logNormEstimate[0] - big) < 25.0  # 110-way merge: a few nats of Monte-Carlo error at N = 100
+
+
+def test_oracle_gaussian_summary_sampler_moments():
+    """orc_node_summaries on a population with a known message: without the transform the node statistics
+    are the mean / SD of N(mu, sigma^2) draws (polar method on the summary stream)."""
+    N = 200_000
+    mu, var = 0.7, 2.25
+
+    class R:  # the fields node_summaries reads
+        state = np.zeros((1, 6, N))
+        anc = np.arange(N, dtype=np.int64)[None, :]
+
+    R.state[0][0][:] = mu
+    R.state[0][1][:] = var
+    csr = d.perfectBinaryTree(0).to_csr() if False else None
+    import types
+
+    one = types.SimpleNamespace(nNodes=1, childOffsets=np.array([0, 0], np.int32), children=np.zeros(0, np.int32),
+                                parent=np.array([-1], np.int32), nChildren=lambda i: 0, depth=lambda: np.zeros(1, np.int32))
+    s = o.node_summaries(R, one, 0, levelCutOffForOutput=1, useTransform=False)
+    assert abs(s["meanMean"] - mu) < 5 * math.sqrt(var / N)
+    assert abs(s["meanSD"] - math.sqrt(var)) < 5 * math.sqrt(var / (2 * N))
