@@ -486,7 +486,10 @@ class DistributedDC:
         import torch
 
         want = os.environ.get("DCSMC_TRANSPORT", "p2p")
-        ok = 1 if (want == "p2p" and dev.type == "cuda" and hasattr(self.engine, "peer_pool_handle")) else 0
+        # CUDA engines map each other's pools with CUDA IPC; the CPU stand-in of the gloo tests emulates peer
+        # memory with POSIX shared memory and says so (hostPeerMemory)
+        can = dev.type == "cuda" or getattr(self.engine, "hostPeerMemory", False)
+        ok = 1 if (want == "p2p" and can and hasattr(self.engine, "peer_pool_handle")) else 0
         if ok:
             try:
                 self._exchange_pool_handles(dist, dev)
@@ -580,7 +583,8 @@ class DistributedDC:
                 account()
         # nobody may start overwriting its pool (next run) while a peer still reads from it
         dist.all_reduce(self._p2pSync)
-        torch.cuda.current_stream(dev).synchronize()
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()  # the barrier must have completed on the host's timeline
         return nvbytes
 
     def _peer_read_bytes(self, child: int) -> int:

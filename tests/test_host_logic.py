@@ -218,6 +218,156 @@ class FakeEngine:
         return I()
 
 
+class FakePeerEngine(FakeEngine):
+    """FakeEngine whose populations live in a POSIX shared-memory 'pool' that peers map and read in place:
+    the same export -> descriptor -> import_peer protocol as the CUDA-IPC path (include/dcsmc.h,
+    "zero-copy sharing"), so DistributedDC._top_levels_p2p runs on CPU over gloo. A rank that reset its pool
+    before its peers finished reading (a missing closing barrier) poisons the slots and changes the root."""
+
+    hostPeerMemory = True
+    SLOT = 32
+
+    def __init__(self, ddc):
+        super().__init__(ddc)
+        from multiprocessing import shared_memory
+
+        self._shm = shared_memory.SharedMemory(create=True, size=self.SLOT * self.nNodes)
+        self._pool = np.ndarray((self.nNodes, 4), dtype=np.float64, buffer=self._shm.buf)
+        self._pool[:] = np.nan
+        self._peers = {}
+        self._remote = {}
+        self.generation = 1
+
+    # pool-resident populations: self.pop[n] is a view into the shared pool
+    def _compute(self, n):
+        kids = self._kids(n)
+        v = np.array([n + 1.0, 0.5 * n, 1.0, -n], dtype=np.float64)
+        for k, c in enumerate(kids):
+            cp = self._remote[c] if c in self._remote else self.pop[c]
+            v = v * 0.75 + (k + 1) * np.roll(cp, k + 1) + 0.001 * cp[0] * v[2]
+        self._pool[n] = v
+        self.pop[n] = self._pool[n]
+        for c in kids:
+            self.pop.pop(c, None)  # released on the host side; exported slots stay readable until the reset
+            self._remote.pop(c, None)
+
+    def _rec(self, n):
+        if n in self.pop or n in self._remote:
+            return
+        for c in self._kids(n):
+            self._rec(c)
+        self._compute(n)
+
+    def reset_populations(self):
+        super().reset_populations()
+        self._pool[:] = np.nan  # a peer still reading now would see NaN
+        self._remote = {}
+
+    def run_nodes(self, nodes):
+        if any(c in self._remote for n in nodes for c in self._kids(n)):
+            import time
+
+            time.sleep(0.05)  # a slow consumer: its producers must still hold the exported populations
+        super().run_nodes(nodes)
+
+    def peer_pool_handle(self):
+        name = self._shm.name.encode()
+        return name + b"\0" * (64 - len(name)), self.generation
+
+    def peer_open(self, peer, handle, generation):
+        from multiprocessing import shared_memory
+
+        shm = shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode())
+        self._peers[peer] = (shm, np.ndarray((self.nNodes, 4), dtype=np.float64, buffer=shm.buf), generation)
+
+    def export(self, nodes):
+        out = b""
+        for n in nodes:
+            assert n in self.pop, f"node {n} is not resident"
+            d_ = np.zeros(16, np.int64)  # 128 bytes: slot index, generation
+            d_[0], d_[1] = n, self.generation
+            out += d_.tobytes()
+        return out
+
+    def import_peer(self, nodes, peers, descs):
+        for k, (n, p_) in enumerate(zip(nodes, peers)):
+            d_ = np.frombuffer(descs[k * 128:(k + 1) * 128], np.int64)
+            assert int(d_[1]) == self._peers[p_][2], "pool generation mismatch"
+            self._remote[n] = self._peers[p_][1][int(d_[0])]  # a VIEW: read in place at run_nodes time
+
+    def all_node_stats(self):
+        st = super().all_node_stats()
+        return st
+
+    def close(self):
+        for shm, _, _ in self._peers.values():
+            shm.close()
+        self._peers = {}
+        self._pool = None
+        self.pop = {}
+        self._remote = {}
+        self._shm.close()
+        self._shm.unlink()
+
+
+def _gloo_worker_p2p(rank, world, port, depth_opt, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows(seed=3, nGroups=5))
+        ddc = d.DistributedDC.createInstance(d.DCOptions(nParticles=4, maximumDistributionDepth=depth_opt),
+                                             d.MultiLevelProposalFactory(dataset=ds), ds.getTree())
+        ddc.engineFactory = FakePeerEngine
+        vals = []
+        for _ in range(3):  # back-to-back runs, no collective in between: only the run's own closing barrier
+            ddc.run()       # protects run k's (slow) readers from run k+1's reset of the producers' pools
+            if rank == ddc.rootOwner:
+                vals.append(float(ddc.engine.pop[0].sum()))
+        vals = vals or [None]
+        final = float(ddc.stats["logScaling"][0])
+        q.put((rank, vals, final, ddc._transportChoice, ddc.lastRun["nvlinkBytes"]))
+        dist.barrier()
+        ddc.engine.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("depth_opt", [1, 2])
+def test_zero_copy_schedule_over_gloo_with_shared_memory_pools(world, depth_opt):
+    """The p2p transport's host logic (descriptor all-gather = barrier, import, run, closing barrier) with
+    POSIX shared memory standing in for NVLink peer memory: same root value as one process, every run."""
+    import torch.multiprocessing as mp
+
+    ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows(seed=3, nGroups=5))
+    single = d.DistributedDC.createInstance(d.DCOptions(nParticles=4), d.MultiLevelProposalFactory(dataset=ds), ds.getTree())
+    single.engineFactory = FakeEngine
+    single.run()
+    expect = float(single.stats["logScaling"][0])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000) + 10 * world + depth_opt
+    procs = [ctx.Process(target=_gloo_worker_p2p, args=(r, world, port, depth_opt, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    owners = 0
+    for rank, vals, final, transport, moved in res:
+        assert transport == "p2p"
+        assert final == expect, (rank, final, expect)
+        if vals != [None]:
+            owners += 1
+            assert vals == [expect] * 3, (rank, vals, expect)
+    assert owners == 1
+    assert sum(r[4] for r in res) > 0
+
+
 def _gloo_worker(rank, world, port, depth_opt, q):
     import torch.distributed as dist
 
