@@ -1,33 +1,9 @@
-# INTEGRATION — binding `libdcsmc.so` from the reference's Java
-
-The reference has no FFI today; a maintainer would add one class, `dc.GpuDistributedDC`, next to
-`dc/DistributedDC.java`, with the same public methods, and keep every other file unchanged. The JVM is
-not available in this build container, so the Java below is shipped as documentation (uncompiled); the
-same call sequence is exercised through `ctypes` by `divide-and-conquer-smc_b200/_ffi.py` and
-`tests/test_gpu_dc_api.py`.
-
-## 1. What replaces what
-
-| reference call (file:line) | C ABI (`include/dcsmc.h`) |
-|---|---|
-| `new DCOptions()` + flags (dc/DCOptions.java:15-45) | `dcsmc_options_default`, `dcsmc_options` (same field names) |
-| `DistributedDC.createInstance(options, proposalFactory, tree)` (DistributedDC.java:58-70) | `dcsmc_create`, `dcsmc_set_tree`, `dcsmc_set_node_seeds`, `dcsmc_set_multilevel_model` / `dcsmc_set_markov_model` |
-| `ddc.start()` (:87-92) | `dcsmc_run` |
-| `DCRecursionTask.run(node,false)` / `run(node,true)` (DCRecursionTask.java:48-75) | `dcsmc_run_subtrees` / `dcsmc_run_nodes` |
-| `DCProcessor.process(populationBeforeResampling, children)` (DCProcessor.java:18) | `dcsmc_node_stats` / `dcsmc_all_node_stats` (ESS, rESS, logNormEstimate, logScaling, resampled) |
-| `ddc.getRootPopulation()` (:107) | `dcsmc_population_copy_to_host(engine, root, …)` |
-| Hazelcast `populations.put/remove` (DCRecursionTask.java:37,113) | on one NVLink node: `dcsmc_peer_pool_handle` / `dcsmc_peer_open` once, then `dcsmc_population_export` → 128-byte descriptor → `dcsmc_population_import_peer` (the consumer's merge kernel reads the peer GPU's memory directly). Otherwise `dcsmc_population_pack/unpack/release` (device buffers; move them with NCCL or `cudaMemcpyPeer`) |
-| impl-1 `printNodeStatistics` / `printDeltaNodeStatistics` (prototype/smc/DivideConquerMCAlgorithm.java:433-507), option `levelCutOffForOutput` (:56) | `dcsmc_options.levelCutOffForOutput`, `dcsmc_node_summary` (meanStats, varStats, deltaStats) |
-| timing rows of `DefaultProcessorFactory` (:41-54) | `dcsmc_last_run_info` (per call), `dcsmc_timer_begin/end` (any sequence of calls) |
-| `Random random` argument (DCProposal.java:28) | `rngMode`: Philox (default), `dcsmc_inject_uniforms`, or `DCSMC_RNG_JAVA` |
-
-## 2. Panama FFM binding (JDK 22+, no native glue code)
-
-The same source is shipped as `integration/java/dc/GpuDistributedDC.java`
-(`tests/test_host_logic.py::test_java_shim_matches_the_abi` keeps it, this section, `include/dcsmc.h` and
-the ctypes mirror in agreement: symbol names, and the field order of `dcsmc_options`).
-
-```java
+// GpuDistributedDC.java — the class a maintainer of alexandrebouchard/divide-and-conquer-smc would add next to
+// src/main/java/dc/DistributedDC.java to run the DC-SMC node step on libdcsmc.so (Panama FFM, JDK 22+).
+// SHIPPED UNCOMPILED: this build environment has no JDK and none of the reference's dependencies
+// (bayonet, briefj, ...); the same call sequence is exercised through ctypes by
+// divide-and-conquer-smc_b200/_ffi.py and tests/test_gpu_dc_api.py. Kept in sync with INTEGRATION.md §2 by
+// tests/test_host_logic.py::test_java_shim_matches_the_abi.
 package dc;
 
 import java.lang.foreign.*;
@@ -135,72 +111,3 @@ public final class GpuDistributedDC<N> {
     }
   }
 }
-```
-
-`dc/DDCMain.java:21-30` then needs a one-line change: `new GpuDistributedDC<>(options, proposalFactory,
-proposalFactory.getDataset().getTree()).start()` instead of `DistributedDC.createInstance(...).start()`;
-`scripts/run-distributed.sh` keeps its flags (`-dataFile … -nParticles … -maximumDistributionDepth …`).
-
-## 3. JNI alternative (JDK 8, the reference's vintage)
-
-```java
-public final class DcsmcJni {
-  static { System.loadLibrary("dcsmc_jni"); }
-  public static native long create(long seed, int nParticles, int scheme, double relEssThreshold, int maxDepth);
-  public static native void setTree(long h, int root, int[] childOffsets, int[] children, int[] hashCodes);
-  public static native void setMultiLevelModel(long h, int[] nTrials, int[] nSuccesses, double variancePrior);
-  public static native void run(long h);
-  public static native double[] nodeStats(long h, int node);          // ess, relEss, logNormEstimate, logScaling, resampled
-  public static native void rootPopulation(long h, double[] state6xN, double[] weights);
-  public static native void destroy(long h);
-}
-```
-
-```c
-/* dcsmc_jni.c — ~60 lines of glue: each native method pins its arrays and forwards to dcsmc.h */
-JNIEXPORT void JNICALL Java_dc_DcsmcJni_setTree(JNIEnv* env, jclass c, jlong h, jint root,
-                                                jintArray off, jintArray ch, jintArray hash) {
-  jint n = (*env)->GetArrayLength(env, off) - 1;
-  jint *o = (*env)->GetIntArrayElements(env, off, 0), *k = (*env)->GetIntArrayElements(env, ch, 0),
-       *s = (*env)->GetIntArrayElements(env, hash, 0);
-  int rc = dcsmc_set_tree((dcsmc_engine*)h, n, root, o, k);
-  if (!rc) rc = dcsmc_set_node_seeds((dcsmc_engine*)h, s);
-  (*env)->ReleaseIntArrayElements(env, off, o, JNI_ABORT); /* … same for ch, hash … */
-  if (rc) (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/RuntimeException"), dcsmc_last_error((dcsmc_engine*)h));
-}
-```
-
-Particles never pass through the JVM heap: only the CSR topology (a few KB), per-leaf counts, per-node
-statistics and — on request — the root population cross the boundary.
-
-## 4. Identical-stream parity runs from Java
-
-To drive both sides with one uniform stream (BASELINE north_star), subclass `java.util.Random` on the
-Java side so that `nextDouble()` returns `u[node][cursor++]`, and have the leaf proposal call
-`seek(particle * S)` before each `propose` (S = `dcsmc_slots_per_particle`); give the same `u[node]` to
-`dcsmc_inject_uniforms`. For internal nodes S = 1, so the Java stream needs no seeking at all: it is
-consumed in exactly the engine's order (N proposal draws, then N darts). Alternatively use
-`DCSMC_RNG_JAVA`, which regenerates `new Random(31*(31+masterRandomSeed)+node.hashCode())` on the device
-for fixed-draw proposals — `tests/test_gpu_dc_api.py::test_java_rng_mode_*` checks it bit for bit against
-the sequential JDK generator restated in the oracle.
-
-## 5. Multi-GPU
-
-One process per GPU. `sharding.make_plan` (or the equivalent ~60 lines in Java) gives each rank its subtree
-roots and, per level above `maximumDistributionDepth`, which rank owns which node and which child
-populations are remote. Ranks call `dcsmc_run_subtrees`; then, level by level:
-
-```
-handle, gen = dcsmc_peer_pool_handle(engine)          // 64 bytes, once per pool generation
-descs       = dcsmc_population_export(engine, myFinishedChildrenNeededElsewhere)   // 128 bytes each
-all_gather(gen | handle | descs)                      // any transport: it is < 10 KB; also the barrier
-dcsmc_peer_open(engine, peerRank, handle, gen)        // no-op when that generation is already mapped
-dcsmc_population_import_peer(engine, remoteChildren, ownerRanks, theirDescs)
-dcsmc_run_nodes(engine, nodesIOwnAtThisLevel)         // reads remote children over NVLink
-```
-
-and one barrier closes the run (a producer must not start the next run while a peer still reads its pool).
-`divide-and-conquer-smc_b200/dc.py::_top_levels_p2p` is this loop over `torch.distributed`. Without CUDA
-IPC (different nodes, container policy) exchange `dcsmc_population_pack` buffers instead (NCCL
-`ncclSend/ncclRecv`, or `cudaMemcpyPeerAsync`), `dcsmc_population_unpack`, then `dcsmc_run_nodes`
-(`DCSMC_TRANSPORT=nccl` selects this path in `dc.py`).

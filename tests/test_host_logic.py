@@ -434,3 +434,36 @@ def test_native_cli_dataset_loader_matches_python_mirror(tmp_path):
     assert r.returncode == 2 and "dataFile is required" in r.stderr
     r = subprocess.run([cli, "-dataFile", str(p), "-resamplingScheme", "SYSTEMATIC"], capture_output=True, text=True)
     assert r.returncode == 2
+
+
+def test_header_is_valid_c99_and_cxx11():
+    """include/dcsmc.h is the boundary a JNI / Panama / cgo shim binds: it must be plain C."""
+    import shutil
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "dcsmc.h")
+    if shutil.which("gcc"):
+        r = subprocess.run(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-pedantic", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    if shutil.which("g++"):
+        r = subprocess.run(["g++", "-fsyntax-only", "-x", "c++", "-std=c++11", "-pedantic", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_java_shim_matches_the_abi():
+    """integration/java/dc/GpuDistributedDC.java (shipped uncompiled, no JDK here) and INTEGRATION.md bind the
+    ABI by name and by struct layout: every symbol they look up is exported, and the OPTIONS layout lists the
+    fields of dcsmc_options in order."""
+    java = open(os.path.join(ROOT, "integration", "java", "dc", "GpuDistributedDC.java")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    body = java[java.index("package dc;"):]
+    assert body.strip() in doc.replace("\r", ""), "INTEGRATION.md §2 and the .java file diverged"
+    looked_up = set(re.findall(r'h\("(dcsmc_[a-z_]+)"', java))
+    assert looked_up and looked_up <= set(_ffi.SYMBOLS), looked_up - set(_ffi.SYMBOLS)
+    hdr = open(os.path.join(ROOT, "include", "dcsmc.h")).read()
+    struct = hdr[hdr.index("typedef struct dcsmc_options {"):hdr.index("} dcsmc_options;")]
+    c_fields = re.findall(r"^\s*(?:int32_t|int64_t|double)\s+(\w+);", struct, flags=re.M)
+    layout = java[java.index("static final StructLayout OPTIONS"):java.index("static final StructLayout NODE_STATS")]
+    j_fields = re.findall(r'withName\("(\w+)"\)', layout)
+    assert j_fields == c_fields, (j_fields, c_fields)
+    assert [f for f, _ in _ffi.Options._fields_] == c_fields
