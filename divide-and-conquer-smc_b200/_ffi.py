@@ -62,6 +62,14 @@ class NodeSummary(C.Structure):
     ]
 
 
+class PlanInfo(C.Structure):
+    _fields_ = [
+        ("poolBytesNeeded", C.c_int64), ("poolBytes", C.c_int64), ("peakBytes", C.c_int64),
+        ("scratchBytes", C.c_int64), ("tableBytes", C.c_int64), ("nodesPlanned", C.c_int64),
+        ("levelBatches", C.c_int32), ("maxBatchNodes", C.c_int32), ("feasible", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class RunInfo(C.Structure):
     _fields_ = [
         ("deviceMs", C.c_double),
@@ -87,7 +95,7 @@ SYMBOLS = [
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
     "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval", "dcsmc_reset_populations",
     "dcsmc_timer_begin", "dcsmc_timer_end",
-    "dcsmc_node_summary", "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
+    "dcsmc_node_summary", "dcsmc_plan_query", "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
 ]
 IPC_HANDLE_BYTES, EXPORT_DESC_BYTES = 64, 128
 
@@ -133,6 +141,7 @@ def lib():
     L.dcsmc_reset_populations.argtypes = [vp]
     L.dcsmc_last_run_info.argtypes = [vp, P(RunInfo)]
     L.dcsmc_node_summary.argtypes = [vp, i32, P(NodeSummary)]
+    L.dcsmc_plan_query.argtypes = [P(Options), i32, P(i32), P(i32), P(i32), i32, i64, P(PlanInfo), C.c_char_p, i32]
     L.dcsmc_peer_pool_handle.argtypes = [vp, vp, P(i64)]
     L.dcsmc_peer_open.argtypes = [vp, i32, vp, i64]
     L.dcsmc_population_export.argtypes = [vp, P(i32), i32, vp]

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -114,6 +115,7 @@ struct dcsmc_engine {
   size_t poolNeed = 0;        // bytes of "everything resident at once" (0 = not computed yet)
   std::map<size_t, size_t> freeBySize;  // free holes below poolTop: offset -> bytes (coalesced)
   size_t poolTop = 0;
+  size_t poolPeak = 0;           // high-water mark of poolTop (dcsmc_plan_query)
   std::vector<Slot> slot;        // per node
   std::vector<char> resident;    // per node
   std::vector<char> imported;    // per node: population installed by dcsmc_population_unpack
@@ -592,6 +594,7 @@ int planRoots(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan) {
       for (auto& s : trial.steps) plan.steps.push_back(std::move(s));
       plan.stepNodes = std::move(trial.stepNodes);
       commitPool(e, saved);
+      e->poolPeak = std::max(e->poolPeak, peak);
       return DCSMC_OK;
     }
     restorePool(e, saved);
@@ -621,6 +624,7 @@ int planRoots(dcsmc_engine* e, const std::vector<int>& roots, Plan& plan) {
     return e->fail(DCSMC_ENOMEM, "population pool (%zu bytes) too small for node %d and its children",
                    e->poolBytes, r);
   plan.stepNodes.push_back(r);
+  e->poolPeak = std::max(e->poolPeak, e->poolTop);
   if (!e->opt.retainPopulations)
     for (int c = e->childOffsets[r]; c < e->childOffsets[r + 1]; ++c) {
       st.releaseAfter.push_back(e->children[c]);
@@ -1908,6 +1912,79 @@ int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node) {
   if (!e) return DCSMC_EINVAL;
   if (node < 0 || node >= e->nNodes || e->resident.empty()) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   poolFree(e, node);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_plan_query(const dcsmc_options* opt, int32_t nNodes, const int32_t* childOffsets,
+                         const int32_t* children, const int32_t* leafKind, int32_t model, int64_t budgetBytes,
+                         dcsmc_plan_info* out, char* err, int32_t errLen) {
+  auto say = [&](const char* msg) {
+    if (err && errLen > 0) snprintf(err, (size_t)errLen, "%s", msg);
+  };
+  if (!opt || !out || nNodes < 1 || !childOffsets) {
+    say("dcsmc_plan_query: bad arguments");
+    return DCSMC_EINVAL;
+  }
+  if (opt->nParticles < 1 || opt->nParticles >= (1 << 24)) {
+    say("nParticles must be in [1, 2^24)");
+    return DCSMC_EINVAL;
+  }
+  memset(out, 0, sizeof *out);
+  // a host-only engine object: no stream, no device memory, never passed to a function that touches CUDA
+  std::unique_ptr<dcsmc_engine> holder(new dcsmc_engine());
+  dcsmc_engine* e = holder.get();
+  e->opt = *opt;
+  int rc = dcsmc_set_tree(e, nNodes, 0, childOffsets, children);
+  if (rc == DCSMC_OK) {
+    if (model == DCSMC_MODEL_MARKOV) {
+      e->model = DCSMC_MODEL_MARKOV;
+      e->nStates = 2;
+    } else {
+      const std::vector<int32_t> zeros(nNodes, 0);  // leaf data do not influence the plan
+      rc = dcsmc_set_multilevel_model(e, leafKind, zeros.data(), zeros.data(), nullptr, 1.0);
+    }
+  }
+  if (rc != DCSMC_OK) {
+    say(e->err.c_str());
+    return rc;
+  }
+  const int N = opt->nParticles;
+  e->Npad = (int)alignUp((size_t)N, 32);
+  e->slot.assign(nNodes, Slot{});
+  e->resident.assign(nNodes, 0);
+  e->imported.assign(nNodes, 0);
+  size_t need = 0;
+  for (int n = 0; n < nNodes; ++n) need += slotBytes(e, n);
+  need = std::max<size_t>(need, 256);
+  e->poolBytes = budgetBytes > 0 ? std::min<size_t>((size_t)budgetBytes, need) : need;
+  e->poolIsBudget = e->poolBytes < need;
+  Plan plan;
+  rc = planRoots(e, std::vector<int>{e->root}, plan);
+  out->poolBytesNeeded = (int64_t)need;
+  out->poolBytes = (int64_t)e->poolBytes;
+  out->feasible = rc == DCSMC_OK ? 1 : 0;
+  if (rc != DCSMC_OK) {
+    say(e->err.c_str());
+    return rc == DCSMC_ENOMEM ? DCSMC_OK : rc;  // "does not fit" is an answer, not an error
+  }
+  size_t maxStep = 0, maxInternalStep = 0;
+  for (auto& s : plan.steps) {
+    maxStep = std::max<size_t>(maxStep, s.count);
+    if (!s.leaf || opt->sumMode == DCSMC_SUM_JAVA) maxInternalStep = std::max<size_t>(maxInternalStep, s.count);
+  }
+  size_t invB = 1;
+  while (invB * 8 < (size_t)N) invB <<= 1;
+  const bool small = N <= SMALLN_MAX && opt->sumMode != DCSMC_SUM_JAVA;  // shared-memory node kernel: no CDF / index scratch
+  size_t scratch = (maxStep * descWordsPerNode(N) + 2 * MAX_CHUNKS + 2) * sizeof(unsigned long long);
+  if (!small) scratch += maxInternalStep * (size_t)e->Npad * sizeof(double) + maxInternalStep * (invB + 1) * sizeof(int32_t);
+  if (opt->resamplingScheme == DCSMC_MULTINOMIAL) scratch += maxStep * (size_t)e->Npad * sizeof(int32_t);
+  out->peakBytes = (int64_t)e->poolPeak;
+  out->scratchBytes = (int64_t)scratch;
+  out->tableBytes = (int64_t)((sizeof(NodeDev) + sizeof(NodeStats) + sizeof(LeafConst) + sizeof(uint64_t) + sizeof(double*) +
+                               sizeof(NodeStatsOut)) * (size_t)nNodes + sizeof(int32_t) * (size_t)(2 * nNodes));
+  out->nodesPlanned = (int64_t)plan.stepNodes.size();
+  out->levelBatches = (int32_t)plan.steps.size();
+  out->maxBatchNodes = (int32_t)maxStep;
   return DCSMC_OK;
 }
 

@@ -13,6 +13,28 @@ def _ptr(a: Optional[np.ndarray], ctype):
     return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
 
 
+def plan_query(csr, *, model: int = F.MODEL_MULTILEVEL, leafKind=None, budgetBytes: int = 0, **opts) -> F.PlanInfo:
+    """dcsmc_plan_query: what the static memory planner would do for this tree — host only, no CUDA device
+    needed. `opts` are dcsmc_options fields (nParticles, resamplingScheme, retainPopulations, ...)."""
+    L = F.lib()
+    o = F.Options()
+    L.dcsmc_options_default(C.byref(o))
+    for k, v in opts.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown option {k}")
+        setattr(o, k, v)
+    off = np.ascontiguousarray(csr.childOffsets, dtype=np.int32)
+    ch = np.ascontiguousarray(csr.children if len(csr.children) else np.zeros(1, np.int32), dtype=np.int32)
+    lk = None if leafKind is None else np.ascontiguousarray(leafKind, dtype=np.int32)
+    info = F.PlanInfo()
+    err = C.create_string_buffer(512)
+    rc = L.dcsmc_plan_query(C.byref(o), csr.nNodes, _ptr(off, C.c_int32), _ptr(ch, C.c_int32), _ptr(lk, C.c_int32),
+                            model, int(budgetBytes), C.byref(info), err, len(err))
+    if rc != 0:
+        raise F.DcsmcError(rc, err.value.decode())
+    return info
+
+
 class Engine:
     def __init__(self, **opts):
         L = F.lib()

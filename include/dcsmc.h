@@ -246,6 +246,29 @@ int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n
 int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, const int32_t* peers,
                                      int32_t n, const void* descs);
 
+/* ---- planning without a device ---------------------------------------------------------
+ * The schedule and the memory plan are a pure function of (options, tree, leaf kinds, pool size): this
+ * entry point runs the planner on the host only — no CUDA device is needed or touched — and reports what
+ * dcsmc_run would do. Use it to size a job (does BASELINE config 5 fit 180 GB per GPU? how many subtree
+ * batches does a memory budget cost?) before allocating anything. */
+typedef struct dcsmc_plan_info {
+  int64_t poolBytesNeeded; /* every population resident at once (the pool dcsmc_run would like) */
+  int64_t poolBytes;       /* the pool the plan was made for: min(needed, budget) */
+  int64_t peakBytes;       /* high-water mark of the plan inside that pool */
+  int64_t scratchBytes;    /* per-step scratch of the largest step: CDF, offspring counts, index, descriptors */
+  int64_t tableBytes;      /* per-node device tables (descriptors, statistics, leaf constants, seeds) */
+  int64_t nodesPlanned;
+  int32_t levelBatches;    /* groups of launches (one per level when everything fits) */
+  int32_t maxBatchNodes;   /* sibling nodes in the largest batch */
+  int32_t feasible;        /* 0: even one node with its children does not fit the budget */
+  int32_t reserved;
+} dcsmc_plan_info;
+/* leafKind: per node (DCSMC_LEAF_*), NULL = all binomial; model: DCSMC_MODEL_*; budgetBytes: 0 = unlimited.
+ * err (optional, errLen bytes) receives the message on failure. */
+int32_t dcsmc_plan_query(const dcsmc_options* opt, int32_t nNodes, const int32_t* childOffsets,
+                         const int32_t* children, const int32_t* leafKind, int32_t model,
+                         int64_t budgetBytes, dcsmc_plan_info* out, char* err, int32_t errLen);
+
 /* ---- measurement ---------------------------------------------------------------------- */
 
 enum {

@@ -467,3 +467,68 @@ def test_java_shim_matches_the_abi():
     j_fields = re.findall(r'withName\("(\w+)"\)', layout)
     assert j_fields == c_fields, (j_fields, c_fields)
     assert [f for f, _ in _ffi.Options._fields_] == c_fields
+
+
+def test_plan_query_runs_the_memory_planner_without_a_device():
+    """dcsmc_plan_query: schedule + memory plan on the host only (this container has no GPU)."""
+    from dcsmc_b200.engine import plan_query
+
+    ds = d.MultiLevelDataset(rows=synth.nys_shaped_rows())
+    csr = ds.getTree().to_csr()
+    N = 100_000
+    full = plan_query(csr, nParticles=N)
+    h = csr.height()
+    nLeaf = sum(1 for i in range(csr.nNodes) if csr.nChildren(i) == 0)
+    assert full.feasible and full.nodesPlanned == csr.nNodes
+    assert full.levelBatches == int(h.max()) + 1 and full.maxBatchNodes == nLeaf  # one batch per level
+    # leaves 20 B / particle, internal nodes 60 B / particle (DESIGN.md §3), slots rounded to 256 B
+    Npad = (N + 31) // 32 * 32
+    assert full.poolBytesNeeded == sum((-(-(Npad * (20 if csr.nChildren(i) == 0 else 60)) // 256)) * 256 for i in range(csr.nNodes))
+    assert full.peakBytes <= full.poolBytes == full.poolBytesNeeded
+    # children are released as soon as their parent consumed them: the peak is below "everything resident"
+    assert full.peakBytes < full.poolBytesNeeded
+    # a quarter of the memory: more, smaller batches; same nodes; never above the budget
+    quarter = plan_query(csr, nParticles=N, budgetBytes=full.poolBytesNeeded // 4)
+    assert quarter.feasible and quarter.nodesPlanned == csr.nNodes
+    assert quarter.levelBatches > full.levelBatches and quarter.maxBatchNodes < full.maxBatchNodes
+    assert quarter.peakBytes <= quarter.poolBytes <= full.poolBytesNeeded // 4
+    assert quarter.scratchBytes < full.scratchBytes
+    # retained populations never leave the pool
+    kept = plan_query(csr, nParticles=N, retainPopulations=1)
+    assert kept.peakBytes == kept.poolBytesNeeded
+    # too small for one node and its children: an answer, not an exception
+    tiny = plan_query(csr, nParticles=N, budgetBytes=1 << 20)
+    assert not tiny.feasible
+    with pytest.raises(_ffi.DcsmcError):
+        plan_query(csr, nParticles=1 << 24)
+
+
+def test_plan_query_baseline_config5_fits_one_b200():
+    """BASELINE config 5: root -> 10 -> 100 -> 100 leaves (1e5 leaves), nParticles = 1e7. Everything resident
+    would be 20.6 TB; with a 140 GiB pool the planner walks the tree in subtree batches of a few
+    level-2 nodes (each 100 leaves x 200 MB) and stays inside the budget."""
+    import types
+
+    from dcsmc_b200.engine import plan_query
+
+    nN = 1 + 10 + 1000 + 100_000
+    kids = {0: list(range(1, 11))}
+    for k in range(10):
+        kids[1 + k] = list(range(11 + 100 * k, 111 + 100 * k))
+    for k in range(1000):
+        kids[11 + k] = list(range(1011 + 100 * k, 1111 + 100 * k))
+    off = np.zeros(nN + 1, np.int32)
+    ch = []
+    for n in range(nN):
+        c = kids.get(n, [])
+        ch += c
+        off[n + 1] = off[n] + len(c)
+    csr = types.SimpleNamespace(nNodes=nN, childOffsets=off, children=np.array(ch, np.int32))
+    N = 10_000_000
+    everything = plan_query(csr, nParticles=N, resamplingScheme=1, relativeEssThreshold=0.5)
+    assert everything.poolBytesNeeded > 20e12 and everything.levelBatches == 4
+    budget = 140 << 30
+    p = plan_query(csr, nParticles=N, resamplingScheme=1, relativeEssThreshold=0.5, budgetBytes=budget)
+    assert p.feasible and p.nodesPlanned == nN
+    assert p.peakBytes <= budget and p.peakBytes + p.scratchBytes + p.tableBytes < 180e9  # one B200
+    assert 100 <= p.maxBatchNodes <= 700 and p.levelBatches > 300
