@@ -146,6 +146,7 @@ void usage() {
       "        [-maximumDistributionDepth <int>] [-nThreadsPerNode 1] [-variancePrior 1.0]\n"
       "        [-clusterSubGroup 1] [-minimumNumberOfClusterMembersToStart 1] [-maximumTimeToWaitInMinutes 1]\n"
       "        [-indexInCluster 1] [-device 0] [-resultsFolder results/latest] [-dumpTree]\n"
+      "        [-memoryBudgetGiB 0] [-planOnly]   (-planOnly: print the schedule and memory plan, no GPU needed)\n"
       "        [-levelCutOffForOutput 0] [-useTransform true]   (posterior summaries of impl-1: meanStats,\n"
       "        varStats, deltaStats for nodes with level < cut-off; the reference's default cut-off is 2)\n"
       "flags are the field names of dc.DCOptions / MultiLevelProposalFactory (dc/DDCMain.java:14-18)");
@@ -158,7 +159,8 @@ int main(int argc, char** argv) {
   dcsmc_options_default(&opt);
   std::string dataFile, results = "results/latest";
   double variancePrior = 1.0;
-  bool dumpTree = false;
+  bool dumpTree = false, planOnly = false;
+  long long memoryBudgetGiB = 0;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     while (!a.empty() && a[0] == '-') a.erase(0, 1);
@@ -171,6 +173,8 @@ int main(int argc, char** argv) {
     };
     if (a == "help" || a == "h") { usage(); return 0; }
     else if (a == "dumpTree") dumpTree = true;
+    else if (a == "planOnly") planOnly = true;
+    else if (a == "memoryBudgetGiB") { memoryBudgetGiB = std::atoll(val()); opt.memoryBudgetBytes = memoryBudgetGiB << 30; }
     else if (a == "dataFile") dataFile = val();
     else if (a == "variancePrior") variancePrior = std::atof(val());
     else if (a == "resultsFolder") results = val();
@@ -208,6 +212,20 @@ int main(int argc, char** argv) {
       std::printf("\n");
     }
     return 0;
+  }
+  if (planOnly) {  // the static memory planner on the host: sizes a job before anything is allocated
+    dcsmc_plan_info pi;
+    char msg[512] = "";
+    const int rc = dcsmc_plan_query(&opt, nN, t.childOffsets.data(), t.children.empty() ? t.childOffsets.data() : t.children.data(),
+                                    nullptr, DCSMC_MODEL_MULTILEVEL, opt.memoryBudgetBytes, &pi, msg, (int)sizeof msg);
+    if (rc) { std::fprintf(stderr, "dcsmc_plan_query: %s\n", msg); return 1; }
+    std::printf("plan: nodes=%d nParticles=%d feasible=%d levelBatches=%d maxBatchNodes=%d\n", nN, opt.nParticles, pi.feasible,
+                pi.levelBatches, pi.maxBatchNodes);
+    std::printf("plan: poolBytesNeeded=%lld poolBytes=%lld peakBytes=%lld scratchBytes=%lld tableBytes=%lld\n",
+                (long long)pi.poolBytesNeeded, (long long)pi.poolBytes, (long long)pi.peakBytes, (long long)pi.scratchBytes,
+                (long long)pi.tableBytes);
+    if (!pi.feasible) std::printf("plan: %s\n", msg);
+    return pi.feasible ? 0 : 3;
   }
   dcsmc_engine* e = nullptr;
   if (dcsmc_create(&opt, &e)) { std::fprintf(stderr, "dcsmc_create: %s\n", dcsmc_last_error(nullptr)); return 1; }

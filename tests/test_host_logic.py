@@ -532,3 +532,26 @@ def test_plan_query_baseline_config5_fits_one_b200():
     assert p.feasible and p.nodesPlanned == nN
     assert p.peakBytes <= budget and p.peakBytes + p.scratchBytes + p.tableBytes < 180e9  # one B200
     assert 100 <= p.maxBatchNodes <= 700 and p.levelBatches > 300
+
+
+def test_native_cli_plan_only_needs_no_gpu(tmp_path):
+    """dcsmc_ddc -planOnly: the reference's flags plus -memoryBudgetGiB, answered by dcsmc_plan_query."""
+    import subprocess
+
+    from dcsmc_b200.engine import plan_query
+
+    rows = synth.nys_shaped_rows()
+    path = tmp_path / "nys.csv"
+    synth.write_csv(rows, str(path))
+    cli = os.path.join(ROOT, "divide-and-conquer-smc_b200", "csrc", "dcsmc_ddc")
+    r = subprocess.run([cli, "-dataFile", str(path), "-nParticles", "1000000", "-memoryBudgetGiB", "40", "-planOnly"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    kv = dict(tok.split("=") for line in r.stdout.splitlines() if line.startswith("plan:") for tok in line.split()[1:] if "=" in tok)
+    ds = d.MultiLevelDataset(rows=rows)
+    want = plan_query(ds.getTree().to_csr(), nParticles=1_000_000, budgetBytes=40 << 30)
+    assert int(kv["levelBatches"]) == want.levelBatches and int(kv["peakBytes"]) == want.peakBytes
+    assert int(kv["poolBytesNeeded"]) == want.poolBytesNeeded and int(kv["feasible"]) == 1
+    r = subprocess.run([cli, "-dataFile", str(path), "-nParticles", "16000000", "-memoryBudgetGiB", "1", "-planOnly"],
+                       capture_output=True, text=True)
+    assert r.returncode == 3 and "feasible=0" in r.stdout
