@@ -16,6 +16,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -130,7 +131,10 @@ struct dcsmc_engine {
   std::vector<int> externalNodes;   // nodes that got an external slot since the last reset
   struct PeerMap { char* base = nullptr; int64_t generation = -1; };
   std::map<int, PeerMap> peers;     // peer engines' pools mapped through CUDA IPC
-  int64_t poolGeneration = 0;       // bumped whenever the pool is (re)allocated
+  // identifies one allocation of the pool: starts from a per-engine random base (a peer process that
+  // destroys its engine and creates a new one must never collide with a mapping a consumer still holds)
+  // and is bumped whenever the pool is (re)allocated
+  int64_t poolGeneration = 0;
   char *dImp = nullptr, *hImp = nullptr;  // dcsmc_population_import_peer staging
   size_t impCap = 0;
   NodeStatsOut *dExport = nullptr, *hExport = nullptr;  // statistics of the last plan (device / pinned host)
@@ -1310,6 +1314,10 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   }
   dcsmc_engine* e = new dcsmc_engine();
   e->opt = *opt;
+  {
+    std::random_device rd;
+    e->poolGeneration = (int64_t)(((uint64_t)rd() & 0x7fffffffULL) << 24);
+  }
   int prLow = 0, prHigh = 0;
   if (cudaSetDevice(opt->device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
   cudaDeviceGetAttribute(&e->smCount, cudaDevAttrMultiProcessorCount, opt->device);
