@@ -95,7 +95,7 @@ SYMBOLS = [
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
     "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval", "dcsmc_reset_populations",
     "dcsmc_timer_begin", "dcsmc_timer_end",
-    "dcsmc_node_summary", "dcsmc_plan_query", "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
+    "dcsmc_node_summary", "dcsmc_plan_query", "dcsmc_host_eval", "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
 ]
 IPC_HANDLE_BYTES, EXPORT_DESC_BYTES = 64, 128
 
@@ -151,6 +151,7 @@ def lib():
     L.dcsmc_profile_enable.argtypes = [vp, i32]
     L.dcsmc_profile_get.argtypes = [vp, i32, P(dbl), P(i64)]
     L.dcsmc_debug_eval.argtypes = [vp, i32, P(dbl), P(dbl), i64]
+    L.dcsmc_host_eval.argtypes = [i32, P(dbl), P(dbl), i64]
     for s in SYMBOLS:
         f = getattr(L, s)
         if s not in ("dcsmc_last_error", "dcsmc_population_packed_bytes"):

@@ -1679,6 +1679,24 @@ int32_t dcsmc_debug_eval(dcsmc_engine* e, int32_t op, const double* x, double* y
   return DCSMC_OK;
 }
 
+// The same header functions compiled for the HOST (csrc/dcsmc_math.cuh is host+device code): lets the CPU test
+// suite check the engine's own fdlibm / Philox against the oracle without a GPU.
+int32_t dcsmc_host_eval(int32_t op, const double* x, double* y, int64_t n) {
+  if (!x || !y || n < 0 || op < 0 || (op & 0xff) > 2) return DCSMC_EINVAL;
+  const PhiloxKeys rk = philox_round_keys(31ULL);
+  for (int64_t i = 0; i < n; ++i) {
+    if ((op & 0xff) == 2) {
+      double u0, u1;
+      const uint64_t idx = (uint64_t)x[i];
+      philox_uniform_pair_rk(rk, op >> 8, 0u, idx >> 1, u0, u1);
+      y[i] = (idx & 1) ? u1 : u0;
+    } else {
+      y[i] = op == 0 ? dc_log(x[i]) : dc_exp(x[i]);
+    }
+  }
+  return DCSMC_OK;
+}
+
 int64_t dcsmc_population_packed_bytes(const dcsmc_engine* e) {
   if (!e) return 0;
   const size_t NP = alignUp((size_t)e->opt.nParticles, 32);

@@ -35,6 +35,16 @@ def plan_query(csr, *, model: int = F.MODEL_MULTILEVEL, leafKind=None, budgetByt
     return info
 
 
+def host_eval(op: int, x: np.ndarray) -> np.ndarray:
+    """dcsmc_host_eval: the engine's own log / exp / Philox (csrc/dcsmc_math.cuh) compiled for the host."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    rc = F.lib().dcsmc_host_eval(op, _ptr(x, C.c_double), _ptr(y, C.c_double), len(x))
+    if rc != 0:
+        raise F.DcsmcError(rc, "dcsmc_host_eval: bad arguments")
+    return y
+
+
 class Engine:
     def __init__(self, **opts):
         L = F.lib()

@@ -209,6 +209,9 @@ int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre,
 /* Parity/debug: evaluate an elementary function of the numerics contract on the DEVICE for n host
  * inputs (op 0: log, 1: exp — the fdlibm algorithms StrictMath specifies). */
 int32_t dcsmc_debug_eval(dcsmc_engine* e, int32_t op, const double* x, double* y, int64_t n);
+/* The same functions from the same header compiled for the host (no device needed): op 0 log, 1 exp,
+ * 2 | node << 8: Philox uniform number (uint64)x[i] of `node`, seed 31. */
+int32_t dcsmc_host_eval(int32_t op, const double* x, double* y, int64_t n);
 
 /* ---- moving populations between engines (replaces Hazelcast populations.put/remove,
  * DCRecursionTask.java:37,113) ---------------------------------------------------------- */

@@ -555,3 +555,51 @@ def test_native_cli_plan_only_needs_no_gpu(tmp_path):
     r = subprocess.run([cli, "-dataFile", str(path), "-nParticles", "16000000", "-memoryBudgetGiB", "1", "-planOnly"],
                        capture_output=True, text=True)
     assert r.returncode == 3 and "feasible=0" in r.stdout
+
+
+def test_engine_math_header_equals_fdlibm_oracle_on_the_host():
+    """csrc/dcsmc_math.cuh is host+device code: its host build (dcsmc_host_eval) must equal the oracle's literal
+    fdlibm bit for bit — the hot path is straight-line code with ONE rare-argument dispatch, so the inputs
+    concentrate on that dispatch: around 1 (|x-1| < 2^-20 boundary), mantissa thresholds of e_log.c
+    (0x6147a, 0x6b851, 0x95f64), powers of two, subnormals, zero, negative, inf, NaN; e_exp.c's 0.5 ln2 /
+    1.5 ln2 / 2^-28 / overflow / underflow boundaries. Same for Philox with precomputed round keys."""
+    import oracle_lib as o
+    from dcsmc_b200.engine import host_eval
+
+    L = o.lib()
+    rng = np.random.default_rng(12)
+
+    def from_hi(hi, lo=0):
+        return np.array([(int(h) << 32) | int(l) for h, l in np.broadcast(hi, lo)], dtype=np.uint64).view(np.float64)
+
+    near1 = 1.0 + np.concatenate([np.arange(-40, 41) * 2.0 ** -22, rng.normal(0, 2.0 ** -20, 20000), rng.normal(0, 1e-9, 5000)])
+    hi_edges = []
+    for e_ in (0x3fe, 0x3ff, 0x400, 0x001, 0x7fe, 0x200):
+        for m in (0x00000, 0x00001, 0x00002, 0xffffd, 0xffffe, 0xfffff, 0x6147a, 0x6147b, 0x61479, 0x6b851, 0x6b850, 0x6b852,
+                  0x6a09e, 0x6a09f, 0x6a09d, 0x95f64 ^ 0xfffff, 0x0a09b, 0x0a09c, 0x0a09d):
+            hi_edges.append((e_ << 20) | m)
+    edges = np.concatenate([from_hi(np.array(hi_edges), 0), from_hi(np.array(hi_edges), 0xffffffff), from_hi(np.array(hi_edges), 1)])
+    logs = np.concatenate([
+        np.exp(rng.uniform(-740, 709, 200000)), rng.uniform(0, 1, 200000), rng.uniform(0.5, 2.0, 100000), near1, edges,
+        2.0 ** np.arange(-1074, 1024, dtype=np.float64), np.array([0.0, -0.0, 5e-324, 2.2250738585072014e-308, 2.2250738585072009e-308,
+                                                                   1.7976931348623157e308, np.inf, -np.inf, -1.0, -5e-324, np.nan])])
+    got = host_eval(0, logs)
+    want = np.array([L.orc_elem_log(o.ELEM_FDLIBM, float(x)) for x in logs])
+    assert np.array_equal(got.view(np.uint64)[~np.isnan(want)], want.view(np.uint64)[~np.isnan(want)])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ln2 = 0.6931471805599453
+    exps = np.concatenate([
+        rng.uniform(-746, 710, 200000), rng.uniform(-2, 2, 200000), rng.normal(0, 1e-3, 20000), rng.normal(0, 2.0 ** -28, 20000),
+        np.array([k * ln2 * s + d_ for k in (0.5, 1.5, 1, 2, 10, 1000) for s in (1, -1) for d_ in (0, 1e-16, -1e-16, 1e-12, -1e-12)]),
+        from_hi(np.array([0x3fd62e42, 0x3fd62e43, 0x3fd62e41, 0x3ff0a2b2, 0x3ff0a2b1, 0x3ff0a2b3, 0x3e300000, 0x3e2fffff, 0x40862e42,
+                          0x40862e41, 0xbfd62e42, 0xbff0a2b2, 0xc0862e42, 0xc0874910, 0xc0874385]), 0),
+        np.array([0.0, -0.0, 709.782712893384, 709.7827128933841, -745.1332191019411, -745.1332191019412, np.inf, -np.inf, np.nan])])
+    got = host_eval(1, exps)
+    want = np.array([L.orc_elem_exp(o.ELEM_FDLIBM, float(x)) for x in exps])
+    assert np.array_equal(got.view(np.uint64)[~np.isnan(want)], want.view(np.uint64)[~np.isnan(want)])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    idx = np.concatenate([np.arange(0, 20000, dtype=np.float64), np.array([2.0 ** 33 + 1, 2.0 ** 40 + 6, 2.0 ** 52 + 3])])
+    for node in (0, 7, 3537):
+        got = host_eval(2 | (node << 8), idx)
+        want = np.array([L.orc_philox_uniform(31, node, int(i)) for i in idx])
+        assert np.array_equal(got, want)
