@@ -5,8 +5,8 @@ prepareNextTask). Pure host logic, no torch: unit-tested on CPU.
 The reference cuts the tree at `maximumDistributionDepth`: every node at that depth (or a leaf
 above it) is an initial task that recurses serially through its whole subtree; nodes above the
 cut become tasks when their last child finishes and fetch the children populations from the
-cluster map. Here the same cut yields (i) subtrees, assigned to ranks by longest-processing-time
-and run level-batched on one GPU each, and (ii) a short, fully static schedule for the nodes above
+cluster map. Here the same cut yields (i) subtrees, assigned to ranks by longest-processing-time (or by a
+contiguous partition when that is as well balanced: siblings then stay together) and run level-batched on one GPU each, and (ii) a short, fully static schedule for the nodes above
 the cut: for each level, which populations move between which ranks and which rank runs which
 node. Per-node random streams are keyed by node id, so the result does not depend on the
 assignment (Doc.java:268).
@@ -59,6 +59,60 @@ def assign_lpt(tasks: List[int], weights: List[int], world: int) -> Dict[int, in
     return owner
 
 
+def assign_contiguous(tasks: List[int], weights: List[int], world: int) -> Dict[int, int]:
+    """Contiguous partition of the subtree roots (they come in depth-first order, so siblings are adjacent)
+    into at most `world` ranges with the smallest possible maximum load. Siblings then share a rank, and the
+    nodes above the cut find most of their children locally instead of reading them over NVLink."""
+    if not tasks:
+        return {}
+    def ranges(cap: int) -> List[List[int]]:
+        out: List[List[int]] = []
+        cur: List[int] = []
+        load = 0
+        for t, w in zip(tasks, weights):
+            if cur and load + w > cap:
+                out.append(cur)
+                cur, load = [], 0
+            cur.append(t)
+            load += w
+        out.append(cur)
+        return out
+
+    lo, hi = max(weights), sum(weights)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if len(ranges(mid)) <= world:
+            hi = mid
+        else:
+            lo = mid + 1
+    owner: Dict[int, int] = {}
+    for r, group in enumerate(ranges(lo)):
+        for t in group:
+            owner[t] = r
+    return owner
+
+
+def _makespan(owner: Dict[int, int], tasks: List[int], weights: List[int], world: int) -> int:
+    load = [0] * world
+    for t, w in zip(tasks, weights):
+        load[owner[t]] += w
+    return max(load)
+
+
+def assign(tasks: List[int], weights: List[int], world: int, slack: float = 0.02) -> Dict[int, int]:
+    """Longest-processing-time gives the best balance, a contiguous partition the best locality (fewest remote
+    children above the cut). Balance decides the run time of the subtrees, locality only the short levels
+    above the cut, so the contiguous partition is taken only when its slowest rank is within `slack` of LPT's:
+    always on regular trees (BASELINE configs 4 and 5), not on the uneven NYS-shaped tree (4-16 % worse)."""
+    lpt = assign_lpt(tasks, weights, world)
+    if not tasks or world <= 1:
+        return lpt
+    contiguous = assign_contiguous(tasks, weights, world)
+    if _makespan(contiguous, tasks, weights, world) <= (1.0 + slack) * _makespan(lpt, tasks, weights, world):
+        return contiguous
+    return lpt
+
+
 @dataclass
 class TopLevel:
     nodes: List[Tuple[int, int]] = field(default_factory=list)            # (node, owner rank)
@@ -81,7 +135,7 @@ def make_plan(csr, maximumDistributionDepth: int, world: int) -> ShardPlan:
     cut = effective_cut_depth(csr, maximumDistributionDepth, world)
     tasks = initial_tasks(csr, cut)
     sizes = csr.subtree_sizes()
-    owner = assign_lpt(tasks, [int(sizes[t]) for t in tasks], world)
+    owner = assign(tasks, [int(sizes[t]) for t in tasks], world)
     node_owner: Dict[int, int] = dict(owner)
     task_set = set(tasks)
     # nodes above the cut = ancestors of task roots

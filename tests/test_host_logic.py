@@ -603,3 +603,55 @@ def test_engine_math_header_equals_fdlibm_oracle_on_the_host():
         got = host_eval(2 | (node << 8), idx)
         want = np.array([L.orc_philox_uniform(31, node, int(i)) for i in idx])
         assert np.array_equal(got, want)
+
+
+def test_subtree_assignment_prefers_locality_when_balance_allows():
+    """sharding.assign: contiguous ranges of sibling subtrees when they balance as well as LPT (regular trees:
+    BASELINE configs 4 and 5), LPT otherwise (the uneven NYS-shaped tree)."""
+    # perfect binary tree, cut at depth 3: 8 equal subtrees
+    csr = d.perfectBinaryTree(6).to_csr()
+    for world in (2, 4, 8):
+        plan = sharding.make_plan(csr, 3, world)
+        owners = [plan.task_owner[t] for t in plan.tasks]
+        assert owners == sorted(owners), owners  # contiguous
+        assert sorted(set(owners)) == list(range(world))
+        moved = sum(len(l.transfers) for l in plan.top_levels)
+        assert moved == world - 1, (world, moved)  # one remote child per rank boundary, nothing else
+    # BASELINE config 5 shape: root -> 10 -> 100 each (cut 2): each depth-1 node keeps its children on <= 2 ranks
+    import types
+
+    kids = {0: list(range(1, 11))}
+    for k in range(10):
+        kids[1 + k] = list(range(11 + 100 * k, 111 + 100 * k))
+    nN = 1011
+    off = np.zeros(nN + 1, np.int32)
+    ch = []
+    parent = np.full(nN, -1, np.int32)
+    for n in range(nN):
+        c = kids.get(n, [])
+        for x in c:
+            parent[x] = n
+        ch += c
+        off[n + 1] = off[n] + len(c)
+    t = d.CsrTree(nodes=list(range(nN)), index={i: i for i in range(nN)}, parent=parent, childOffsets=off,
+                  children=np.array(ch, np.int32), javaHash=np.zeros(nN, np.int32))
+    plan = sharding.make_plan(t, 1 if False else 2, 8)
+    assert len(plan.tasks) == 1000
+    load = [0] * 8
+    for tk in plan.tasks:
+        load[plan.task_owner[tk]] += 1
+    assert max(load) == 125
+    for n1 in range(1, 11):
+        assert len({plan.task_owner[c] for c in kids[n1]}) <= 2
+    remote = sum(len(l.transfers) for l in plan.top_levels)
+    lpt = sharding.assign_lpt(plan.tasks, [1] * 1000, 8)
+    remote_lpt = sum(1 for n1 in range(1, 11) for c in kids[n1]
+                     if lpt[c] != max(range(8), key=lambda r: (sum(1 for x in kids[n1] if lpt[x] == r), -r)))
+    assert remote < 0.3 * remote_lpt, (remote, remote_lpt)  # 208 vs 870 remote children
+    # the uneven NYS-shaped tree keeps the better-balanced LPT assignment
+    ds = d.MultiLevelDataset(rows=synth.nys_shaped_rows())
+    csr = ds.getTree().to_csr()
+    sizes = csr.subtree_sizes()
+    tasks = sharding.initial_tasks(csr, 2)
+    w = [int(sizes[x]) for x in tasks]
+    assert sharding.assign(tasks, w, 8) == sharding.assign_lpt(tasks, w, 8)
