@@ -141,7 +141,7 @@ def lib():
     L.dcsmc_reset_populations.argtypes = [vp]
     L.dcsmc_last_run_info.argtypes = [vp, P(RunInfo)]
     L.dcsmc_node_summary.argtypes = [vp, i32, P(NodeSummary)]
-    L.dcsmc_plan_query.argtypes = [P(Options), i32, P(i32), P(i32), P(i32), i32, i64, P(PlanInfo), C.c_char_p, i32]
+    L.dcsmc_plan_query.argtypes = [P(Options), i32, P(i32), P(i32), P(i32), i32, P(i32), i32, i64, P(PlanInfo), C.c_char_p, i32]
     L.dcsmc_peer_pool_handle.argtypes = [vp, vp, P(i64)]
     L.dcsmc_peer_open.argtypes = [vp, i32, vp, i64]
     L.dcsmc_population_export.argtypes = [vp, P(i32), i32, vp]

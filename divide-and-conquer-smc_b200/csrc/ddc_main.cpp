@@ -217,7 +217,7 @@ int main(int argc, char** argv) {
     dcsmc_plan_info pi;
     char msg[512] = "";
     const int rc = dcsmc_plan_query(&opt, nN, t.childOffsets.data(), t.children.empty() ? t.childOffsets.data() : t.children.data(),
-                                    nullptr, DCSMC_MODEL_MULTILEVEL, opt.memoryBudgetBytes, &pi, msg, (int)sizeof msg);
+                                    nullptr, DCSMC_MODEL_MULTILEVEL, nullptr, 0, opt.memoryBudgetBytes, &pi, msg, (int)sizeof msg);
     if (rc) { std::fprintf(stderr, "dcsmc_plan_query: %s\n", msg); return 1; }
     std::printf("plan: nodes=%d nParticles=%d feasible=%d levelBatches=%d maxBatchNodes=%d\n", nN, opt.nParticles, pi.feasible,
                 pi.levelBatches, pi.maxBatchNodes);

@@ -1942,8 +1942,8 @@ int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node) {
 }
 
 int32_t dcsmc_plan_query(const dcsmc_options* opt, int32_t nNodes, const int32_t* childOffsets,
-                         const int32_t* children, const int32_t* leafKind, int32_t model, int64_t budgetBytes,
-                         dcsmc_plan_info* out, char* err, int32_t errLen) {
+                         const int32_t* children, const int32_t* leafKind, int32_t model, const int32_t* roots,
+                         int32_t nRoots, int64_t budgetBytes, dcsmc_plan_info* out, char* err, int32_t errLen) {
   auto say = [&](const char* msg) {
     if (err && errLen > 0) snprintf(err, (size_t)errLen, "%s", msg);
   };
@@ -1979,13 +1979,29 @@ int32_t dcsmc_plan_query(const dcsmc_options* opt, int32_t nNodes, const int32_t
   e->slot.assign(nNodes, Slot{});
   e->resident.assign(nNodes, 0);
   e->imported.assign(nNodes, 0);
-  size_t need = 0;
-  for (int n = 0; n < nNodes; ++n) need += slotBytes(e, n);
+  std::vector<int> rootSet;
+  if (roots && nRoots > 0) {
+    for (int k = 0; k < nRoots; ++k) {
+      if (roots[k] < 0 || roots[k] >= nNodes) {
+        say("dcsmc_plan_query: bad root");
+        return DCSMC_EINVAL;
+      }
+      rootSet.push_back(roots[k]);
+    }
+  } else {
+    rootSet.push_back(e->root);
+  }
+  size_t need = 0;  // every population of the planned subtrees resident at once
+  {
+    std::vector<int> nodes;
+    for (int r : rootSet) collectSubtree(e, r, nodes);
+    for (int n : nodes) need += slotBytes(e, n);
+  }
   need = std::max<size_t>(need, 256);
   e->poolBytes = budgetBytes > 0 ? std::min<size_t>((size_t)budgetBytes, need) : need;
   e->poolIsBudget = e->poolBytes < need;
   Plan plan;
-  rc = planRoots(e, std::vector<int>{e->root}, plan);
+  rc = planRoots(e, rootSet, plan);
   out->poolBytesNeeded = (int64_t)need;
   out->poolBytes = (int64_t)e->poolBytes;
   out->feasible = rc == DCSMC_OK ? 1 : 0;

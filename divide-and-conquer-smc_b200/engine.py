@@ -13,9 +13,10 @@ def _ptr(a: Optional[np.ndarray], ctype):
     return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
 
 
-def plan_query(csr, *, model: int = F.MODEL_MULTILEVEL, leafKind=None, budgetBytes: int = 0, **opts) -> F.PlanInfo:
-    """dcsmc_plan_query: what the static memory planner would do for this tree — host only, no CUDA device
-    needed. `opts` are dcsmc_options fields (nParticles, resamplingScheme, retainPopulations, ...)."""
+def plan_query(csr, *, model: int = F.MODEL_MULTILEVEL, leafKind=None, roots=None, budgetBytes: int = 0, **opts) -> F.PlanInfo:
+    """dcsmc_plan_query: what the static memory planner would do for this tree (or for the subtrees `roots`,
+    one rank's share of a sharded run) — host only, no CUDA device needed. `opts` are dcsmc_options fields
+    (nParticles, resamplingScheme, retainPopulations, ...)."""
     L = F.lib()
     o = F.Options()
     L.dcsmc_options_default(C.byref(o))
@@ -28,8 +29,9 @@ def plan_query(csr, *, model: int = F.MODEL_MULTILEVEL, leafKind=None, budgetByt
     lk = None if leafKind is None else np.ascontiguousarray(leafKind, dtype=np.int32)
     info = F.PlanInfo()
     err = C.create_string_buffer(512)
+    rt = None if roots is None else np.ascontiguousarray(roots, dtype=np.int32)
     rc = L.dcsmc_plan_query(C.byref(o), csr.nNodes, _ptr(off, C.c_int32), _ptr(ch, C.c_int32), _ptr(lk, C.c_int32),
-                            model, int(budgetBytes), C.byref(info), err, len(err))
+                            model, _ptr(rt, C.c_int32), 0 if rt is None else len(rt), int(budgetBytes), C.byref(info), err, len(err))
     if rc != 0:
         raise F.DcsmcError(rc, err.value.decode())
     return info

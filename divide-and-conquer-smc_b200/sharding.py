@@ -164,3 +164,16 @@ def make_plan(csr, maximumDistributionDepth: int, world: int) -> ShardPlan:
                 lvl.transfers.append((c, node_owner[c], own))
     assert all(t in task_set or t in seen for t in node_owner)
     return ShardPlan(cut, tasks, owner, node_owner, [levels[h] for h in sorted(levels)])
+
+
+def plan_memory(csr, plan: ShardPlan, budgetBytes: int = 0, **engine_options):
+    """Per-rank schedule and memory plan of a sharded run (dcsmc_plan_query on each rank's subtrees): host only,
+    no device needed. Returns one PlanInfo per rank (None for a rank without subtrees)."""
+    from .engine import plan_query
+
+    world = max(plan.task_owner.values(), default=-1) + 1
+    out = []
+    for r in range(world):
+        mine = plan.my_tasks(r)
+        out.append(plan_query(csr, roots=mine, budgetBytes=budgetBytes, **engine_options) if mine else None)
+    return out

@@ -266,11 +266,13 @@ typedef struct dcsmc_plan_info {
   int32_t feasible;        /* 0: even one node with its children does not fit the budget */
   int32_t reserved;
 } dcsmc_plan_info;
-/* leafKind: per node (DCSMC_LEAF_*), NULL = all binomial; model: DCSMC_MODEL_*; budgetBytes: 0 = unlimited.
- * err (optional, errLen bytes) receives the message on failure. */
+/* leafKind: per node (DCSMC_LEAF_*), NULL = all binomial; model: DCSMC_MODEL_*; roots/nRoots: the
+ * subtrees to plan as dcsmc_run_subtrees would (one rank's share of a sharded run), NULL/0 = the whole
+ * tree as dcsmc_run; budgetBytes: 0 = unlimited. err (optional, errLen bytes) receives the message on failure. */
 int32_t dcsmc_plan_query(const dcsmc_options* opt, int32_t nNodes, const int32_t* childOffsets,
                          const int32_t* children, const int32_t* leafKind, int32_t model,
-                         int64_t budgetBytes, dcsmc_plan_info* out, char* err, int32_t errLen);
+                         const int32_t* roots, int32_t nRoots, int64_t budgetBytes, dcsmc_plan_info* out,
+                         char* err, int32_t errLen);
 
 /* ---- measurement ---------------------------------------------------------------------- */
 

@@ -532,6 +532,19 @@ def test_plan_query_baseline_config5_fits_one_b200():
     assert p.feasible and p.nodesPlanned == nN
     assert p.peakBytes <= budget and p.peakBytes + p.scratchBytes + p.tableBytes < 180e9  # one B200
     assert 100 <= p.maxBatchNodes <= 700 and p.levelBatches > 300
+    # the same job on 8 GPUs, cut at depth 2: every rank gets 125 of the 1000 subtrees and fits its 140 GiB pool
+    parent = np.full(nN, -1, np.int32)
+    for a, cs in kids.items():
+        for c in cs:
+            parent[c] = a
+    tree = d.CsrTree(nodes=list(range(nN)), index={i: i for i in range(nN)}, parent=parent, childOffsets=off,
+                     children=np.array(ch, np.int32), javaHash=np.zeros(nN, np.int32))
+    shard = sharding.make_plan(tree, 2, 8)
+    per_rank = sharding.plan_memory(tree, shard, budgetBytes=budget, nParticles=N, resamplingScheme=1, relativeEssThreshold=0.5)
+    assert len(per_rank) == 8
+    for info in per_rank:
+        assert info.feasible and info.nodesPlanned == 125 * 101 and info.peakBytes <= budget
+        assert info.poolBytesNeeded == pytest.approx(everything.poolBytesNeeded / 8, rel=0.01)
 
 
 def test_native_cli_plan_only_needs_no_gpu(tmp_path):
