@@ -277,3 +277,72 @@ def test_oracle_gaussian_summary_sampler_moments():
     s = o.node_summaries(R, one, 0, levelCutOffForOutput=1, useTransform=False)
     assert abs(s["meanMean"] - mu) < 5 * math.sqrt(var / N)
     assert abs(s["meanSD"] - math.sqrt(var)) < 5 * math.sqrt(var / (2 * N))
+
+
+# ---- mathematical ground truth for the parts of the path the reference never tests (fixtures 2-3) ----
+
+@pytest.mark.parametrize("C_", [1, 2, 3, 7])
+@pytest.mark.parametrize("zero_child_variance", [True, False])
+def test_brownian_combine_equals_the_closed_form_marginal_likelihood(C_, zero_child_variance):
+    """BrownianModelCalculator.combine (BrownianModelCalculator.java:18-41, 86-115): child c carries the message
+    N(x_c; m_c, s_c) and logLik L_c; the parent value x has a flat prior and x_c | x ~ N(x, v). Folding pairwise must
+    give the posterior of x (precision-weighted mean, 1 / sum of precisions) and
+    logLik = sum_c L_c + log INT prod_c N(m_c; x, s_c + v) dx, which has the closed form below."""
+    L = o.lib()
+    rng = np.random.default_rng(100 + C_)
+    m = rng.normal(0, 2, C_)
+    s_ = np.zeros(C_) if zero_child_variance else rng.uniform(0.05, 3.0, C_)
+    ll = rng.normal(-3, 1, C_)
+    v = 0.7
+    out = np.zeros(3)
+    dp = C.POINTER(C.c_double)
+    for mode in (o.ELEM_LIBM, o.ELEM_FDLIBM):
+        L.orc_brownian_combine(mode, C_, m.ctypes.data_as(dp), s_.ctypes.data_as(dp), ll.ctypes.data_as(dp), v, out.ctypes.data_as(dp))
+        if C_ == 1:  # :23-27: the branch only adds its variance
+            assert out[0] == m[0] and out[1] == s_[0] + v and out[2] == ll[0]
+            continue
+        sig2 = s_ + v
+        P = np.sum(1.0 / sig2)
+        mean = np.sum(m / sig2) / P
+        logint = (-0.5 * np.sum(np.log(2 * np.pi * sig2)) + 0.5 * np.log(2 * np.pi / P)
+                  - 0.5 * (np.sum(m * m / sig2) - np.sum(m / sig2) ** 2 / P))
+        assert out[0] == pytest.approx(mean, rel=1e-12, abs=1e-13)
+        assert out[1] == pytest.approx(1.0 / P, rel=1e-12)
+        assert out[2] == pytest.approx(np.sum(ll) + logint, rel=1e-12, abs=1e-12)
+
+
+def test_two_leaf_binomial_tree_logz_converges_to_quadrature():
+    """One parent, two binomial leaves. In the reference's accounting (MultiLevelLeafProposal.java:40: leaf weight 0,
+    the Beta normaliser is knowingly dropped) the estimator targets
+        Z = E[ INT N(x_1; x, v) N(x_2; x, v) dx ],  x_c = logit p_c,  p_c ~ Beta(1+s_c, 1+n_c-s_c),  v ~ Exp(rate),
+    and INT Exp(v; r) N(d; 0, 2v) dv = sqrt(r)/2 * exp(-sqrt(r)|d|) (a Gaussian scale mixture is a Laplace density),
+    so log Z is a smooth 2-D integral, done here by Gauss-Legendre quadrature. The oracle's logZ must converge to it."""
+    from math import lgamma
+
+    rows = [["NY", "a", "40", "13"], ["NY", "b", "25", "17"]]  # the root merges two leaves directly
+    ds = d.MultiLevelDataset(rows=rows)
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    assert csr.nNodes == 3 and csr.nChildren(0) == 2
+    (n1, s1), (n2, s2) = [(int(nT[i]), int(nS[i])) for i in (1, 2)]
+    rate = 1.0  # MultiLevelProposalFactory.variancePrior default
+    x, w = np.polynomial.legendre.leggauss(1200)
+    p = 0.5 * (x + 1.0)
+    w = 0.5 * w
+
+    def beta_pdf(p_, a, b):
+        return np.exp(lgamma(a + b) - lgamma(a) - lgamma(b) + (a - 1) * np.log(p_) + (b - 1) * np.log1p(-p_))
+
+    f1 = beta_pdf(p, 1 + s1, 1 + n1 - s1) * w
+    f2 = beta_pdf(p, 1 + s2, 1 + n2 - s2) * w
+    assert abs(f1.sum() - 1) < 1e-10 and abs(f2.sum() - 1) < 1e-10
+    lg = np.log(p) - np.log1p(-p)
+    dmat = np.abs(lg[:, None] - lg[None, :])
+    Z = float(f1 @ (0.5 * np.sqrt(rate) * np.exp(-np.sqrt(rate) * dmat)) @ f2)
+    want = np.log(Z)
+    est = []
+    for seed in (31, 32, 33, 34):
+        r = o.run(csr, 200_000, masterRandomSeed=seed, resamplingScheme=o.MULTINOMIAL, rngMode=o.RNG_PHILOX,
+                  sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
+        est.append(r.logNormEstimate[0])
+    assert abs(np.mean(est) - want) < 0.02, (est, want)
