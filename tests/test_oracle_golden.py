@@ -346,3 +346,20 @@ def test_two_leaf_binomial_tree_logz_converges_to_quadrature():
                   sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
         est.append(r.logNormEstimate[0])
     assert abs(np.mean(est) - want) < 0.02, (est, want)
+
+
+def test_impl1_and_impl2_accounting_agree_on_the_same_draws():
+    """SURVEY §8c fixture 5. impl-1 (DivideConquerMCAlgorithm.java:360-361, 404-406: logZ_n = sum_c logZ_c +
+    LSE(lw) - log N, always resample) and impl-2 (DCRecursion.java:55-73 + ParticlePopulation: logScaling with the
+    children's 1/N weights folded into the log weights, logNormEstimate = logScaling - log N) are the same
+    estimator; on identical node-keyed draws every node's logZ must agree to rounding."""
+    from dcsmc_b200 import synth
+
+    ds = d.MultiLevelDataset(rows=synth.small_multilevel_rows())
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    kw = dict(resamplingScheme=o.MULTINOMIAL, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS)
+    r2 = o.run(csr, 5000, impl=2, **kw)
+    r1 = o.run(csr, 5000, impl=1, **kw)
+    assert np.max(np.abs(r2.logNormEstimate - r1.logNormEstimate)) < 1e-12 * max(1.0, abs(r2.logNormEstimate[0]))
+    assert np.array_equal(r1.ess, r2.ess)
