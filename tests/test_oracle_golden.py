@@ -362,4 +362,4 @@ def test_impl1_and_impl2_accounting_agree_on_the_same_draws():
     r2 = o.run(csr, 5000, impl=2, **kw)
     r1 = o.run(csr, 5000, impl=1, **kw)
     assert np.max(np.abs(r2.logNormEstimate - r1.logNormEstimate)) < 1e-12 * max(1.0, abs(r2.logNormEstimate[0]))
-    assert np.array_equal(r1.ess, r2.ess)
+    assert np.allclose(r1.ess, r2.ess, rtol=1e-9, atol=0)  # the constant -C log N shifts log weights before exp
