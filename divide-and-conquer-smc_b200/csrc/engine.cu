@@ -236,14 +236,15 @@ size_t slotBytes(const dcsmc_engine* e, int n) {
 
 void poolFree(dcsmc_engine* e, int n);
 
-// Population pool: a bump pointer (poolTop) plus coalesced free holes below it. Best fit over the
-// holes first, then the hole touching poolTop is extended, then fresh space. All of this runs at
-// plan time on the host; the device only ever sees final addresses.
 // bytes of an unpacked population: always the internal layout (6 columns + ancestors + logw)
 size_t importBytes(const dcsmc_engine* e) {
   const size_t NP = (size_t)e->Npad;
   return alignUp(e->model == DCSMC_MODEL_MARKOV ? NP * 16 : NP * 60, 256);
 }
+
+// Population pool: a bump pointer (poolTop) plus coalesced free holes below it. Best fit over the
+// holes first, then the hole touching poolTop is extended, then fresh space. All of this runs at
+// plan time on the host; the device only ever sees final addresses.
 
 bool poolAlloc(dcsmc_engine* e, int n) {
   poolFree(e, n);  // recomputing a node reuses nothing of its old population
