@@ -668,3 +668,55 @@ def test_subtree_assignment_prefers_locality_when_balance_allows():
     tasks = sharding.initial_tasks(csr, 2)
     w = [int(sizes[x]) for x in tasks]
     assert sharding.assign(tasks, w, 8) == sharding.assign_lpt(tasks, w, 8)
+
+
+def _gloo_worker_binary(rank, world, port, peer, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tree = d.perfectBinaryTree(5)
+        T = np.array([[0.8, 0.2], [0.2, 0.8]])
+        ddc = d.DistributedDC.createInstance(d.DCOptions(nParticles=4, maximumDistributionDepth=3),
+                                             d.MarkovChainNaiveProposalFactory(T, np.array([0.5, 0.5])), tree)
+        ddc.engineFactory = FakePeerEngine if peer else FakeEngine
+        ddc.run()
+        ddc.run()
+        levels_without_transfers = sum(1 for lvl in ddc.plan.top_levels if not lvl.transfers)
+        q.put((rank, float(ddc.stats["logScaling"][0]), levels_without_transfers, ddc._transportChoice))
+        dist.barrier()
+        if peer:
+            ddc.engine.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("peer", [True, False])
+def test_regular_tree_keeps_siblings_together_and_skips_exchanges(peer):
+    """Perfect binary tree, cut at depth 3, 2 ranks: the contiguous assignment leaves whole levels above the cut
+    without any remote child (no descriptor exchange, no send/recv there); only the root has one. Both
+    transports must still reproduce the single-process value."""
+    import torch.multiprocessing as mp
+
+    tree = d.perfectBinaryTree(5)
+    T = np.array([[0.8, 0.2], [0.2, 0.8]])
+    single = d.DistributedDC.createInstance(d.DCOptions(nParticles=4), d.MarkovChainNaiveProposalFactory(T, np.array([0.5, 0.5])), tree)
+    single.engineFactory = FakeEngine
+    single.run()
+    expect = float(single.stats["logScaling"][0])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000) + (1 if peer else 0)
+    procs = [ctx.Process(target=_gloo_worker_binary, args=(r, 2, port, peer, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, val, quiet_levels, transport in res:
+        assert val == expect, (rank, val, expect)
+        assert quiet_levels == 2  # depth-2 and depth-1 nodes find both children on their own rank
+        assert transport == ("p2p" if peer else "nccl")
