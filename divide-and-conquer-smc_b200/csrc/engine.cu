@@ -189,9 +189,12 @@ struct dcsmc_engine {
 #define CK(call)                                                                              \
   do {                                                                                        \
     cudaError_t _e = (call);                                                                  \
-    if (_e != cudaSuccess)                                                                    \
+    if (_e != cudaSuccess) {                                                                  \
+      (void)cudaGetLastError(); /* reported here: do not leave it pending for the next call (e.g. a refused \
+                                   cudaIpcOpenMemHandle must not poison the NCCL fallback) */  \
       return e->fail(DCSMC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),     \
                      __FILE__, __LINE__);                                                     \
+    }                                                                                         \
   } while (0)
 
 namespace {
