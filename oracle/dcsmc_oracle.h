@@ -9,9 +9,15 @@
  *     seeding: PINNED by the reference's one recorded run (Doc.java:282), reproduced by
  *     tests/test_oracle_golden.py to every printed digit.
  *   - hierarchical-binomial model (Beta leaf sampler, BrownianModelCalculator,
- *     Exponential proposal) and STRATIFIED: PARITY UNPINNED — the reference holds no
- *     test, golden vector or fixture for them; pinned only by this repo's closed-form
- *     fixtures.
+ *     Exponential proposal), STRATIFIED and the impl-1 posterior summaries
+ *     (orc_node_summaries): PARITY UNPINNED — the reference holds no test, golden vector or
+ *     fixture for them; tied to mathematics by this repo's own fixtures
+ *     (tests/test_oracle_golden.py: closed-form Gaussian marginal likelihood for combine,
+ *     2-D quadrature of a two-leaf binomial tree's logZ, moments of the Gaussian sampler)
+ *     and to themselves by the committed vectors of tests/golden/.
+ *   - ONE deliberate extension beyond the reference (DESIGN.md "Known deviations"): where the
+ *     linear-space product of the children's weights underflows to exactly 0 (the reference
+ *     then returns log 0 = -inf for every particle), the sum of the logs is used instead.
  */
 #ifndef DCSMC_ORACLE_H
 #define DCSMC_ORACLE_H
