@@ -15,6 +15,8 @@ RNG_PHILOX, RNG_INJECTED, RNG_JAVA = 0, 1, 2
 MODEL_MULTILEVEL, MODEL_MARKOV = 0, 1
 LEAF_BINOMIAL, LEAF_GAUSS_OBS = 0, 1
 SUM_EXACT, SUM_JAVA = 0, 1
+SAMPLE_NATURAL, SAMPLE_MEAN, SAMPLE_VAR, SAMPLE_DELTA0 = 0, 1, 2, 3
+ABI_VERSION = 3
 K_NAMES = ["leaf", "internal", "scan", "finalize", "darts", "resample", "gather", "markov"]
 
 
@@ -38,7 +40,7 @@ class Options(C.Structure):
         ("levelCutOffForOutput", C.c_int32),
         ("memoryBudgetBytes", C.c_int64),
         ("useTransform", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("retainSamples", C.c_int32),
     ]
 
 
@@ -59,6 +61,16 @@ class NodeSummary(C.Structure):
         ("varMean", C.c_double), ("varSD", C.c_double),
         ("deltaMean", C.c_double), ("deltaSD", C.c_double),
         ("hasMean", C.c_int32), ("hasVar", C.c_int32), ("hasDelta", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class PopulationView(C.Structure):
+    _fields_ = [
+        ("state", C.c_void_p), ("istate", C.c_void_p), ("logWeights", C.c_void_p), ("ancestors", C.c_void_p),
+        ("stride", C.c_int64), ("nParticles", C.c_int32), ("nColumns", C.c_int32), ("resampled", C.c_int32),
+        ("onPeer", C.c_int32), ("constantObservation", C.c_int32), ("reserved", C.c_int32),
+        ("observation", C.c_double), ("logScaling", C.c_double), ("maxLogWeight", C.c_double),
+        ("sumExp", C.c_double), ("ess", C.c_double),
     ]
 
 
@@ -95,6 +107,7 @@ SYMBOLS = [
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
     "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval", "dcsmc_reset_populations",
     "dcsmc_timer_begin", "dcsmc_timer_end",
+    "dcsmc_node_samples", "dcsmc_node_times", "dcsmc_population_view",
     "dcsmc_node_summary", "dcsmc_plan_query", "dcsmc_host_eval", "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
 ]
 IPC_HANDLE_BYTES, EXPORT_DESC_BYTES = 64, 128
@@ -141,9 +154,12 @@ def lib():
     L.dcsmc_reset_populations.argtypes = [vp]
     L.dcsmc_last_run_info.argtypes = [vp, P(RunInfo)]
     L.dcsmc_node_summary.argtypes = [vp, i32, P(NodeSummary)]
+    L.dcsmc_node_samples.argtypes = [vp, i32, i32, P(dbl)]
+    L.dcsmc_node_times.argtypes = [vp, P(dbl)]
+    L.dcsmc_population_view.argtypes = [vp, i32, P(PopulationView)]
     L.dcsmc_plan_query.argtypes = [P(Options), i32, P(i32), P(i32), P(i32), i32, P(i32), i32, i64, P(PlanInfo), C.c_char_p, i32]
-    L.dcsmc_peer_pool_handle.argtypes = [vp, vp, P(i64)]
-    L.dcsmc_peer_open.argtypes = [vp, i32, vp, i64]
+    L.dcsmc_peer_pool_handle.argtypes = [vp, vp, P(i64), P(i64)]
+    L.dcsmc_peer_open.argtypes = [vp, i32, vp, i64, i64]
     L.dcsmc_population_export.argtypes = [vp, P(i32), i32, vp]
     L.dcsmc_population_import_peer.argtypes = [vp, P(i32), P(i32), i32, vp]
     L.dcsmc_timer_begin.argtypes = [vp]

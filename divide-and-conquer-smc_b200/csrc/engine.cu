@@ -107,6 +107,7 @@ struct dcsmc_engine {
   uint64_t* dJavaState = nullptr;
   double *dMarkovT = nullptr, *dMarkovPrior = nullptr;
   bool tablesDirty = true;
+  bool leafDirty = false;  // only the leaf data changed (same tree, same leaf kinds): re-upload dLeaf, keep plans
   size_t tableNodesCap = 0, tableEdgesCap = 0;  // sizes the device tables were allocated for
 
   // population pool
@@ -129,14 +130,17 @@ struct dcsmc_engine {
   std::vector<NodeStatsOut> hOut;   // per node: last fetched record (incl. m, S for exports)
   std::vector<int> statNodes;       // nodes whose hStats entry was written since the last reset
   std::vector<int> externalNodes;   // nodes that got an external slot since the last reset
-  struct PeerMap { char* base = nullptr; int64_t generation = -1; };
+  struct PeerMap { char* base = nullptr; int64_t generation = -1; int64_t bytes = 0; };
   std::map<int, PeerMap> peers;     // peer engines' pools mapped through CUDA IPC
   // identifies one allocation of the pool: starts from a per-engine random base (a peer process that
   // destroys its engine and creates a new one must never collide with a mapping a consumer still holds)
   // and is bumped whenever the pool is (re)allocated
   int64_t poolGeneration = 0;
   char *dImp = nullptr, *hImp = nullptr;  // dcsmc_population_import_peer staging
+  LeafConst* hLeafStage = nullptr;        // pinned staging of the leaf table
+  size_t leafStageCap = 0;
   size_t impCap = 0;
+  cudaEvent_t evImp = nullptr;            // the last upload out of hImp
   NodeStatsOut *dExport = nullptr, *hExport = nullptr;  // statistics of the last plan (device / pinned host)
   size_t exportCap = 0;
   cudaEvent_t evT0 = nullptr, evT1 = nullptr;           // dcsmc_timer_begin / dcsmc_timer_end
@@ -145,8 +149,11 @@ struct dcsmc_engine {
   // posterior summaries (levelCutOffForOutput > 0)
   std::vector<int32_t> depth;        // level() of every node
   NodeSummary* dSumm = nullptr;      // per node
-  double* dSumScratch = nullptr;     // sample series of one summary batch
+  double* dSumScratch = nullptr;     // sample series of one summary batch (or of every summary node: retainSamples)
   size_t sumScratchCap = 0;          // in doubles
+  std::vector<int64_t> sampleBase;   // retainSamples: first series of a node inside dSumScratch (-1: none)
+  size_t sampleSeriesTotal = 0;
+  std::vector<double> hNodeMs;       // per node: device time of its level batch / nodes of the batch (profiled runs)
 
   // scratch
   double* dCdf = nullptr;
@@ -173,7 +180,9 @@ struct dcsmc_engine {
   bool profile = false;
   double profMs[DCSMC_K_COUNT] = {0};
   int64_t profLaunches[DCSMC_K_COUNT] = {0};
-  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> profEvents;
+  struct ProfEvent { int cls, step; cudaEvent_t a, b; };
+  std::vector<ProfEvent> profEvents;
+  int curStep = -1;  // level batch being launched (index into the plan's steps)
 
   int fail(int code, const char* fmt, ...) const {
     char buf[512];
@@ -390,8 +399,30 @@ void clearPlanCache(dcsmc_engine* e) {
   e->devicePlan = nullptr;
 }
 
+// per-leaf constants of the model (the per-run INPUT DATA: trial / success counts or observations). Staged in
+// pinned memory so the copy is asynchronous; the previous copy has completed (every run ends with a sync).
+int uploadLeafTable(dcsmc_engine* e) {
+  const int nN = e->nNodes;
+  if ((size_t)nN > e->leafStageCap) {
+    if (e->hLeafStage) cudaFreeHost(e->hLeafStage);
+    e->hLeafStage = nullptr;
+    e->leafStageCap = 0;
+    CK(cudaMallocHost((void**)&e->hLeafStage, sizeof(LeafConst) * (size_t)nN));
+    e->leafStageCap = (size_t)nN;
+  }
+  LeafConst* lc = e->hLeafStage;
+  if (e->model == DCSMC_MODEL_MULTILEVEL)
+    for (int n = 0; n < nN; ++n) leafConstFor(e, n, lc[n]);
+  else
+    memset(lc, 0, sizeof(LeafConst) * nN);
+  CK(cudaMemcpyAsync(e->dLeaf, lc, sizeof(LeafConst) * nN, cudaMemcpyHostToDevice, e->stream));
+  e->pendingH2D += (int64_t)(sizeof(LeafConst) * nN);
+  e->leafDirty = false;
+  return DCSMC_OK;
+}
+
 int uploadTables(dcsmc_engine* e) {
-  if (!e->tablesDirty) return DCSMC_OK;
+  if (!e->tablesDirty) return e->leafDirty ? uploadLeafTable(e) : DCSMC_OK;
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
   if (e->model < 0) return e->fail(DCSMC_ESTATE, "no proposal model set (dcsmc_set_*_model)");
   const int nN = e->nNodes;
@@ -420,13 +451,9 @@ int uploadTables(dcsmc_engine* e) {
   }
   CK(cudaMemcpyAsync(e->dChildren, e->children.data(), sizeof(int32_t) * e->children.size(),
                      cudaMemcpyHostToDevice, e->stream));
-  e->pendingH2D += (int64_t)(sizeof(int32_t) * e->children.size() + (sizeof(LeafConst) + sizeof(uint64_t)) * nN);
-  std::vector<LeafConst> lc(nN);
-  if (e->model == DCSMC_MODEL_MULTILEVEL)
-    for (int n = 0; n < nN; ++n) leafConstFor(e, n, lc[n]);
-  else
-    memset(lc.data(), 0, sizeof(LeafConst) * nN);
-  CK(cudaMemcpyAsync(e->dLeaf, lc.data(), sizeof(LeafConst) * nN, cudaMemcpyHostToDevice, e->stream));
+  e->pendingH2D += (int64_t)(sizeof(int32_t) * e->children.size() + sizeof(uint64_t) * nN);
+  int rcLeaf;
+  if ((rcLeaf = uploadLeafTable(e))) return rcLeaf;
   std::vector<uint64_t> js(nN, 0);
   for (int n = 0; n < nN; ++n)
     js[n] = java_scramble(java_node_seed(e->opt.masterRandomSeed, e->javaHash.empty() ? 0 : e->javaHash[n]));
@@ -660,7 +687,7 @@ struct ProfScope {
   ~ProfScope() {
     if (e->profile) {
       cudaEventRecord(b, s);
-      e->profEvents.push_back({cls, {a, b}});
+      e->profEvents.push_back({cls, e->curStep, a, b});
     }
   }
 };
@@ -705,7 +732,8 @@ bool summaryReportsDeltas(const dcsmc_engine* e, int n) {
   return e->depth[n] + 1 < e->opt.levelCutOffForOutput && nChildrenOf(e, n) > 0;
 }
 int summarySeries(const dcsmc_engine* e, int n) {
-  return 1 + (nodeKind(e, n) == KIND_INTERNAL ? 1 : 0) + (summaryReportsDeltas(e, n) ? nChildrenOf(e, n) : 0);
+  return 1 + (nodeKind(e, n) == KIND_INTERNAL ? 1 : 0) + (summaryReportsDeltas(e, n) ? nChildrenOf(e, n) : 0) +
+         (e->opt.retainSamples ? 1 : 0);
 }
 // uniforms of a node's summary stream (injected mode): 2 per attempt, maxAtt attempts, 2+C draws per particle
 int64_t summaryUniforms(const dcsmc_engine* e, int n) {
@@ -728,21 +756,26 @@ int launchSummaries(dcsmc_engine* e, RunCtx& c, const Step& st, cudaStream_t s) 
   while (k < st.count) {
     SumBatch b;
     memset(&b, 0, sizeof b);
-    int series = 0;
+    // retained samples: every summary node of the plan owns a fixed range of the store (sampleBase, set by
+    // executePlan); otherwise the scratch is reused batch after batch
+    const bool keepS = e->opt.retainSamples != 0;
+    int series = 0, first = 0;
     for (; k < st.count && b.n < SUM_BATCH; ++k) {
       const int n = nodes[k];
       if (e->depth[n] >= e->opt.levelCutOffForOutput) continue;
       const int ns = summarySeries(e, n);
-      if (b.n > 0 && (size_t)(series + ns) > maxSeries) break;
+      if (!keepS && b.n > 0 && (size_t)(series + ns) > maxSeries) break;
+      if (keepS && b.n == 0) first = (int)e->sampleBase[n];
+      if (keepS && b.n > 0 && (int)e->sampleBase[n] != first + series) break;  // ranges of a batch must be contiguous
       b.node[b.n] = n;
-      b.base[b.n] = series;
+      b.base[b.n] = first + series;
       b.delta[b.n] = summaryReportsDeltas(e, n) ? 1 : 0;
       series += ns;
       b.n++;
     }
     if (b.n == 0) continue;
-    b.base[b.n] = series;
-    const size_t need = (size_t)series * c.Npad;
+    b.base[b.n] = first + series;
+    const size_t need = keepS ? e->sampleSeriesTotal * (size_t)c.Npad : (size_t)series * c.Npad;
     if (need > e->sumScratchCap) {  // first (uncaptured) execution of a plan sizes the scratch
       if (e->dSumScratch) cudaFree(e->dSumScratch);
       e->dSumScratch = nullptr;
@@ -943,6 +976,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.summ = e->dSumm;
   c.sumScratch = e->dSumScratch;
   c.useTransform = e->opt.useTransform;
+  c.retainSamples = e->opt.retainSamples ? 1 : 0;
   return DCSMC_OK;
 }
 
@@ -1015,6 +1049,20 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   CK(grow((void**)&e->dInvTable, e->invTableCap, std::max<size_t>(1, maxInternalStep * ((size_t)e->invB + 1)), sizeof(int32_t)));
   if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL)
     CK(grow((void**)&e->dOffspring, e->offspringCap, maxStep * (size_t)e->Npad, sizeof(int32_t)));
+  if (e->opt.retainSamples && e->opt.levelCutOffForOutput > 0 && e->model == DCSMC_MODEL_MULTILEVEL) {
+    // every summary node of the plan owns a fixed range of the sample store, in launch order
+    if ((int)e->sampleBase.size() != e->nNodes) e->sampleBase.assign(e->nNodes, -1);
+    size_t total = 0;
+    for (auto& s : plan.steps)
+      for (int k = 0; k < s.count; ++k) {
+        const int n = plan.stepNodes[s.offset + k];
+        if (e->depth[n] >= e->opt.levelCutOffForOutput) continue;
+        e->sampleBase[n] = (int64_t)total;
+        total += (size_t)summarySeries(e, n);
+      }
+    e->sampleSeriesTotal = total;
+    CK(grow((void**)&e->dSumScratch, e->sumScratchCap, std::max<size_t>(1, total * (size_t)e->Npad), sizeof(double)));
+  }
   bool descriptorsOnDevice = descriptorsValid(e, cached);
   if (cached != nullptr) e->descDirty.clear();
   {
@@ -1067,7 +1115,9 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     }
     e->evNext = 0;
     cudaEvent_t chainDone = nullptr;  // last chain work of the previous level batch
+    int stepIdx = 0;
     for (auto& s : plan.steps) {
+      e->curStep = stepIdx++;
       int nCh = 1;
       if (overlap) nCh = std::max(1, std::min({e->overlapChunks, MAX_CHUNKS, s.count / 8}));
       if (chainDone) {  // children must be complete (and the scratch free) before this level starts
@@ -1180,16 +1230,25 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   }
   e->statNodes.insert(e->statNodes.end(), plan.stepNodes.begin(), plan.stepNodes.end());
   if (e->profile) {
+    // per level batch: the device time of its launches, shared equally by the sibling nodes that ran in it
+    // (what DefaultProcessorFactory reports as iterationProposalTime, DefaultProcessorFactory.java:41-50)
+    std::vector<double> stepMs(plan.steps.size(), 0.0);
     for (auto& pe : e->profEvents) {
       float t = 0;
-      cudaEventElapsedTime(&t, pe.second.first, pe.second.second);
-      e->profMs[pe.first] += t;
-      e->profLaunches[pe.first]++;
-      cudaEventDestroy(pe.second.first);
-      cudaEventDestroy(pe.second.second);
+      cudaEventElapsedTime(&t, pe.a, pe.b);
+      e->profMs[pe.cls] += t;
+      e->profLaunches[pe.cls]++;
+      if (pe.step >= 0 && pe.step < (int)stepMs.size()) stepMs[pe.step] += t;
+      cudaEventDestroy(pe.a);
+      cudaEventDestroy(pe.b);
     }
     e->profEvents.clear();
+    if ((int)e->hNodeMs.size() != e->nNodes) e->hNodeMs.assign(e->nNodes, 0.0);
+    for (size_t k = 0; k < plan.steps.size(); ++k)
+      for (int j = 0; j < plan.steps[k].count; ++j)
+        e->hNodeMs[plan.stepNodes[plan.steps[k].offset + j]] = stepMs[k] / std::max(1, plan.steps[k].count);
   }
+  e->curStep = -1;
   return DCSMC_OK;
 }
 
@@ -1286,6 +1345,7 @@ int32_t dcsmc_options_default(dcsmc_options* o) {
   o->levelCutOffForOutput = 0;  // reference default 2 (DivideConquerMCAlgorithm.java:56); opt-in here
   o->useTransform = 1;          // MultiLevelModelOptions.useTransform (:47)
   o->memoryBudgetBytes = 0;
+  o->retainSamples = 0;
   return DCSMC_OK;
 }
 
@@ -1362,11 +1422,13 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   chk("peer mappings");
   if (e->hImp) cudaFreeHost(e->hImp);
   if (e->dImp) cudaFree(e->dImp);
+  if (e->hLeafStage) cudaFreeHost(e->hLeafStage);
   chk("import staging");
   if (e->hExport) cudaFreeHost(e->hExport);
   chk("export staging (host)");
   if (e->dExport) cudaFree(e->dExport);
   chk("export staging (device)");
+  if (e->evImp) cudaEventDestroy(e->evImp);
   if (e->evT0) cudaEventDestroy(e->evT0);
   if (e->evT1) cudaEventDestroy(e->evT1);
   chk("timer events");
@@ -1398,6 +1460,12 @@ int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root, const int3
   if (!e) return DCSMC_EINVAL;
   if (nNodes < 1 || !childOffsets || root < 0 || root >= nNodes)
     return e->fail(DCSMC_EINVAL, "dcsmc_set_tree: bad arguments");
+  // The same topology again (a caller that re-sends its tree with every data set): device tables, node seeds,
+  // memory plans and captured graphs all stay valid — only the model data that follows is new.
+  if (e->nNodes == nNodes && e->root == root && (int)e->childOffsets.size() == nNodes + 1 &&
+      memcmp(e->childOffsets.data(), childOffsets, sizeof(int32_t) * (size_t)(nNodes + 1)) == 0 &&
+      (nNodes == 1 || (children && memcmp(e->children.data(), children, sizeof(int32_t) * (size_t)(nNodes - 1)) == 0)))
+    return DCSMC_OK;
   if (childOffsets[0] != 0) return e->fail(DCSMC_EINVAL, "childOffsets[0] must be 0");
   const int nEdges = childOffsets[nNodes];
   if (nEdges != nNodes - 1) return e->fail(DCSMC_EINVAL, "a tree with %d nodes needs %d edges, got %d", nNodes, nNodes - 1, nEdges);
@@ -1424,6 +1492,18 @@ int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root, const int3
     const int n = order[k];
     height[parent[n]] = std::max(height[parent[n]], height[n] + 1);
   }
+  // per-node host state of the previous tree is meaningless now (and possibly shorter than the new tree)
+  for (Slot& sl : e->slot)
+    if (sl.external && !sl.peer) e->importFree.push_back(sl.external);
+  e->slot.clear();
+  e->resident.clear();
+  e->imported.clear();
+  e->hStats.clear();
+  e->hOut.clear();
+  e->statNodes.clear();
+  e->externalNodes.clear();
+  e->freeBySize.clear();
+  e->poolTop = 0;
   e->nNodes = nNodes;
   e->root = root;
   e->childOffsets.assign(childOffsets, childOffsets + nNodes + 1);
@@ -1445,6 +1525,8 @@ int32_t dcsmc_set_node_seeds(dcsmc_engine* e, const int32_t* h) {
   if (!e) return DCSMC_EINVAL;
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree first");
   if (!h) return e->fail(DCSMC_EINVAL, "null hash codes");
+  if ((int)e->javaHash.size() == e->nNodes && memcmp(e->javaHash.data(), h, sizeof(int32_t) * (size_t)e->nNodes) == 0)
+    return DCSMC_OK;
   e->javaHash.assign(h, h + e->nNodes);
   e->tablesDirty = true;
   return DCSMC_OK;
@@ -1456,6 +1538,8 @@ int32_t dcsmc_set_multilevel_model(dcsmc_engine* e, const int32_t* leafKind, con
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree first");
   if (!(variancePrior > 0)) return e->fail(DCSMC_EINVAL, "variancePrior must be > 0");
   const int nN = e->nNodes;
+  const std::vector<int32_t> oldKind = e->leafKind;
+  const bool sameFamily = e->model == DCSMC_MODEL_MULTILEVEL && e->rate == variancePrior && !e->tablesDirty;
   e->leafKind.assign(nN, DCSMC_LEAF_BINOMIAL);
   if (leafKind) e->leafKind.assign(leafKind, leafKind + nN);
   e->nTrials.assign(nN, 0);
@@ -1477,7 +1561,12 @@ int32_t dcsmc_set_multilevel_model(dcsmc_engine* e, const int32_t* leafKind, con
   }
   e->model = DCSMC_MODEL_MULTILEVEL;
   e->rate = variancePrior;
-  e->tablesDirty = true;
+  // the memory plan depends on the leaf KINDS only (observed leaves hold no population); new counts /
+  // observations on the same kinds are new input data for the same plan
+  if (sameFamily && oldKind == e->leafKind)
+    e->leafDirty = true;
+  else
+    e->tablesDirty = true;
   return DCSMC_OK;
 }
 
@@ -1530,6 +1619,22 @@ int32_t dcsmc_run_subtrees(dcsmc_engine* e, const int32_t* roots, int32_t nRoots
 }
 
 int32_t dcsmc_run_nodes(dcsmc_engine* e, const int32_t* nodes, int32_t nNodes) {
+  if (!e) return DCSMC_EINVAL;
+  if (!nodes || nNodes < 0) return e->fail(DCSMC_EINVAL, "bad nodes");
+  // DCRecursionTask.getChildrenPopulationsFromCluster (:108-115) fails when a child population is missing; a
+  // silent recomputation of the child's subtree would hide a missed transfer
+  for (int k = 0; k < nNodes; ++k) {
+    const int n = nodes[k];
+    if (n < 0 || n >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", n);
+    for (int c = e->childOffsets[n]; c < e->childOffsets[n + 1]; ++c) {
+      const int ch = e->children[c];
+      bool inSet = false;
+      for (int j = 0; j < nNodes && !inSet; ++j) inSet = nodes[j] == ch;
+      if (!inSet && (e->resident.empty() || !e->resident[ch]))
+        return e->fail(DCSMC_ESTATE, "node %d: the population of child %d is not resident (dcsmc_run_subtrees, "
+                                      "dcsmc_population_unpack or dcsmc_population_import_peer first)", n, ch);
+    }
+  }
   // children resident => collectSubtree stops at them, so this is the same planner
   return dcsmc_run_subtrees(e, nodes, nNodes);
 }
@@ -1574,10 +1679,74 @@ int32_t dcsmc_node_summary(dcsmc_engine* e, int32_t node, dcsmc_node_summary_t* 
   return DCSMC_OK;
 }
 
+int32_t dcsmc_node_samples(dcsmc_engine* e, int32_t node, int32_t which, double* out) {
+  if (!e || !out) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  if (!e->opt.retainSamples || e->opt.levelCutOffForOutput <= 0 || e->dSumScratch == nullptr ||
+      (int)e->sampleBase.size() != e->nNodes || e->sampleBase[node] < 0)
+    return e->fail(DCSMC_ESTATE, "no retained samples for node %d (retainSamples = 1, level() < levelCutOffForOutput, "
+                                 "computed by the last run)", node);
+  if ((int)e->hStats.size() != e->nNodes || !e->hStats[node].done) return e->fail(DCSMC_ESTATE, "node %d not computed", node);
+  if (!e->hStats[node].resampled) return e->fail(DCSMC_ESTATE, "node %d was not resampled: no samples (statistics assume equal weights)", node);
+  const bool internal = nodeKind(e, node) == KIND_INTERNAL;
+  const int nS = summarySeries(e, node);
+  int series;  // layout of k_summary_samples: [mean][var][delta 0..C-1][natural]
+  if (which == DCSMC_SAMPLE_NATURAL) series = nS - 1;
+  else if (which == DCSMC_SAMPLE_MEAN) series = 0;
+  else if (which == DCSMC_SAMPLE_VAR && internal) series = 1;
+  else if (which >= DCSMC_SAMPLE_DELTA0 && summaryReportsDeltas(e, node) && which - DCSMC_SAMPLE_DELTA0 < nChildrenOf(e, node))
+    series = (internal ? 2 : 1) + (which - DCSMC_SAMPLE_DELTA0);
+  else return e->fail(DCSMC_EINVAL, "node %d has no sample series %d", node, which);
+  CK(cudaSetDevice(e->opt.device));
+  CK(cudaMemcpyAsync(out, e->dSumScratch + ((size_t)e->sampleBase[node] + (size_t)series) * (size_t)e->Npad,
+                     sizeof(double) * (size_t)e->opt.nParticles, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_node_times(const dcsmc_engine* e, double* msPerNode) {
+  if (!e || !msPerNode) return DCSMC_EINVAL;
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
+  if ((int)e->hNodeMs.size() != e->nNodes) {
+    memset(msPerNode, 0, sizeof(double) * (size_t)e->nNodes);
+    return DCSMC_OK;
+  }
+  memcpy(msPerNode, e->hNodeMs.data(), sizeof(double) * (size_t)e->nNodes);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_population_view(dcsmc_engine* e, int32_t node, dcsmc_population_view_t* out) {
+  if (!e || !out) return DCSMC_EINVAL;
+  if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
+    return e->fail(DCSMC_ESTATE, "population of node %d is not resident (consumed by its parent, or not computed)", node);
+  memset(out, 0, sizeof *out);
+  fillNodeDev(e, node);
+  const NodeDev& d = e->hNodes[node];
+  const NodeStatsOut& h = e->hOut[node];
+  const bool constLeaf = skipObservedLeaves(e) && d.kind == KIND_LEAF_GAUSS;
+  out->nParticles = e->opt.nParticles;
+  out->stride = e->Npad;
+  out->state = constLeaf ? nullptr : d.state;
+  out->nColumns = d.state == nullptr || constLeaf ? 0 : (d.kind == KIND_INTERNAL ? 6 : 2);
+  out->istate = d.istate;
+  out->logWeights = d.logw;
+  out->resampled = h.resampled == RES_WEIGHTED ? 0 : 1;
+  out->ancestors = (h.resampled == RES_ANCESTORS && !constLeaf) ? d.anc : nullptr;
+  out->onPeer = e->slot[node].peer ? 1 : 0;
+  out->constantObservation = constLeaf ? 1 : 0;
+  out->observation = (!e->leafObs.empty() && d.kind == KIND_LEAF_GAUSS) ? e->leafObs[node] : 0.0;
+  out->logScaling = h.logScaling;
+  out->maxLogWeight = h.m;
+  out->sumExp = h.S;
+  out->ess = h.ess;
+  return DCSMC_OK;
+}
+
 int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* state, int32_t* istate, double* weights) {
   if (!e) return DCSMC_EINVAL;
   if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
-  if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+  if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
     return e->fail(DCSMC_ESTATE, "population of node %d is not resident (consumed by its parent, or not computed)", node);
   CK(cudaSetDevice(e->opt.device));
   const int N = e->opt.nParticles;
@@ -1616,7 +1785,7 @@ int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre, i
   if (!e) return DCSMC_EINVAL;
   if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   if (!e->opt.retainPopulations) return e->fail(DCSMC_ESTATE, "dcsmc_debug_copy_node needs retainPopulations=1");
-  if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+  if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
     return e->fail(DCSMC_ESTATE, "node %d not computed", node);
   CK(cudaSetDevice(e->opt.device));
   const int N = e->opt.nParticles;
@@ -1710,7 +1879,7 @@ int64_t dcsmc_population_packed_bytes(const dcsmc_engine* e) {
 int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t node, void* deviceDst) {
   if (!e) return DCSMC_EINVAL;
   if (node < 0 || node >= e->nNodes || !deviceDst) return e->fail(DCSMC_EINVAL, "dcsmc_population_pack: bad arguments");
-  if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+  if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
     return e->fail(DCSMC_ESTATE, "population of node %d is not resident", node);
   CK(cudaSetDevice(e->opt.device));
   RunCtx c;
@@ -1773,12 +1942,17 @@ struct ExportDesc {
   int64_t generation;   // of that pool
   double m, S, ess, relEss, logScaling, logZ;
   int32_t resampled, done;
-  char pad[DCSMC_EXPORT_DESC_BYTES - 80];
+  int64_t slotBytes;    // bytes of the population: offset + slotBytes must lie inside the owner's pool
+  int32_t model;        // DCSMC_MODEL_* — fixes the column layout together with `kind`
+  int32_t kind;         // KIND_* of the node on the owner (internal: 6 columns + logw; leaf: 2 columns)
+  int32_t node;         // node id on the owner (must equal the importing id: one tree, one numbering)
+  int32_t skipObs;      // the owner does not materialise observed leaves
+  char pad[DCSMC_EXPORT_DESC_BYTES - 104];
 };
 static_assert(sizeof(ExportDesc) == DCSMC_EXPORT_DESC_BYTES, "export descriptor size");
 
-int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generation) {
-  if (!e || !handle || !generation) return DCSMC_EINVAL;
+int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generation, int64_t* poolBytes) {
+  if (!e || !handle || !generation || !poolBytes) return DCSMC_EINVAL;
   static_assert(sizeof(cudaIpcMemHandle_t) == DCSMC_IPC_HANDLE_BYTES, "IPC handle size");
   int rc;
   if ((rc = prepare(e))) return rc;  // allocates the pool
@@ -1786,14 +1960,18 @@ int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generatio
   CK(cudaIpcGetMemHandle(&h, e->pool));
   memcpy(handle, &h, sizeof h);
   *generation = e->poolGeneration;
+  *poolBytes = (int64_t)e->poolBytes;
   return DCSMC_OK;
 }
 
-int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64_t generation) {
-  if (!e || !handle || peer < 0) return DCSMC_EINVAL;
+int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64_t generation, int64_t poolBytes) {
+  if (!e || !handle || peer < 0 || poolBytes < 0) return DCSMC_EINVAL;
   CK(cudaSetDevice(e->opt.device));
   dcsmc_engine::PeerMap& pm = e->peers[peer];
-  if (pm.base && pm.generation == generation) return DCSMC_OK;
+  if (pm.base && pm.generation == generation) {
+    pm.bytes = poolBytes;
+    return DCSMC_OK;
+  }
   if (pm.base) {
     cudaIpcCloseMemHandle(pm.base);
     pm.base = nullptr;
@@ -1804,6 +1982,7 @@ int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64
   CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   pm.base = static_cast<char*>(p);
   pm.generation = generation;
+  pm.bytes = poolBytes;
   return DCSMC_OK;
 }
 
@@ -1813,7 +1992,7 @@ int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n
   for (int k = 0; k < n; ++k) {
     const int node = nodes[k];
     if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
-    if (e->resident.empty() || !e->resident[node] || !e->hStats[node].done)
+    if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
       return e->fail(DCSMC_ESTATE, "population of node %d is not resident", node);
     if (e->slot[node].external)
       return e->fail(DCSMC_ESTATE, "node %d is itself an imported population; only pool residents can be exported", node);
@@ -1831,7 +2010,12 @@ int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n
     d.logScaling = h.logScaling;
     d.logZ = h.logZ;
     d.resampled = h.resampled;
-    d.done = 1;
+    d.done = h.done;
+    d.slotBytes = (int64_t)e->slot[node].bytes;
+    d.model = e->model;
+    d.kind = nodeKind(e, node);
+    d.node = node;
+    d.skipObs = skipObservedLeaves(e) ? 1 : 0;
     out[k] = d;
   }
   return DCSMC_OK;
@@ -1844,8 +2028,34 @@ int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, cons
   int rc;
   if ((rc = prepare(e))) return rc;
   const ExportDesc* in = static_cast<const ExportDesc*>(descs);
+  // pass 1: validate EVERY descriptor before any state changes — a descriptor is foreign input (another process
+  // wrote it, a collective carried it): it must describe a finished population of the same model and layout
+  // that lies inside the mapped pool of that peer
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    const ExportDesc& d = in[k];
+    if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+    if (d.magic != PACK_MAGIC || d.N != e->opt.nParticles)
+      return e->fail(DCSMC_EINVAL, "exported population of node %d does not match this engine (magic/N)", node);
+    if (!d.done) return e->fail(DCSMC_EINVAL, "exported population of node %d is not finished (done = 0)", node);
+    if (d.node != node || d.model != e->model || d.kind != nodeKind(e, node) || d.skipObs != (skipObservedLeaves(e) ? 1 : 0))
+      return e->fail(DCSMC_EINVAL, "exported population of node %d has another layout (node %d, model %d, kind %d, skipObs %d)",
+                     node, d.node, d.model, d.kind, d.skipObs);
+    if (d.resampled != RES_WEIGHTED && d.resampled != RES_ANCESTORS && d.resampled != RES_MATERIALISED)
+      return e->fail(DCSMC_EINVAL, "exported population of node %d: bad resampling state %d", node, d.resampled);
+    auto it = e->peers.find(peerIds[k]);
+    if (it == e->peers.end() || !it->second.base || it->second.generation != d.generation)
+      return e->fail(DCSMC_ESTATE, "pool of peer %d (generation %lld) is not mapped: call dcsmc_peer_open", peerIds[k],
+                     (long long)d.generation);
+    if (d.slotBytes != (int64_t)slotBytes(e, node) || d.offset < 0 || d.offset % 256 != 0 ||
+        d.offset + d.slotBytes > it->second.bytes)
+      return e->fail(DCSMC_EINVAL, "exported population of node %d lies outside the pool of peer %d (offset %lld, %lld bytes, pool %lld)",
+                     node, peerIds[k], (long long)d.offset, (long long)d.slotBytes, (long long)it->second.bytes);
+  }
   const size_t oNd = alignUp(sizeof(int32_t) * n, 256), oSt = oNd + alignUp(sizeof(NodeDev) * n, 256),
                total = oSt + alignUp(sizeof(NodeStats) * n, 256);
+  // the pinned staging buffer is reused: the previous upload must have left it
+  if (e->evImp) CK(cudaEventSynchronize(e->evImp));
   if (total > e->impCap) {
     if (e->dImp) cudaFree(e->dImp);
     if (e->hImp) cudaFreeHost(e->hImp);
@@ -1855,22 +2065,18 @@ int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, cons
     CK(cudaMallocHost((void**)&e->hImp, total));
     e->impCap = total;
   }
+  if (!e->evImp) CK(cudaEventCreateWithFlags(&e->evImp, cudaEventDisableTiming));
   int32_t* hIds = reinterpret_cast<int32_t*>(e->hImp);
   NodeDev* hNd = reinterpret_cast<NodeDev*>(e->hImp + oNd);
   NodeStats* hSt = reinterpret_cast<NodeStats*>(e->hImp + oSt);
+  // pass 2: install
   for (int k = 0; k < n; ++k) {
     const int node = nodes[k];
     const ExportDesc& d = in[k];
-    if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
-    if (d.magic != PACK_MAGIC || d.N != e->opt.nParticles)
-      return e->fail(DCSMC_EINVAL, "exported population of node %d does not match this engine (magic/N)", node);
-    auto it = e->peers.find(peerIds[k]);
-    if (it == e->peers.end() || !it->second.base || it->second.generation != d.generation)
-      return e->fail(DCSMC_ESTATE, "pool of peer %d (generation %lld) is not mapped: call dcsmc_peer_open", peerIds[k],
-                     (long long)d.generation);
+    const dcsmc_engine::PeerMap& pm = e->peers[peerIds[k]];
     poolFree(e, node);
     Slot sl;
-    sl.external = it->second.base + d.offset;
+    sl.external = pm.base + d.offset;
     sl.peer = true;
     e->slot[node] = sl;
     e->externalNodes.push_back(node);
@@ -1905,6 +2111,7 @@ int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, cons
     ho.m = d.m; ho.S = d.S; ho.resampled = d.resampled; ho.done = 1;
   }
   CK(cudaMemcpyAsync(e->dImp, e->hImp, total, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaEventRecord(e->evImp, e->stream));
   e->info.kernelLaunches++;
   k_scatter_import<<<(n + 127) / 128, 128, 0, e->stream>>>(e->dNodes, e->dStats, reinterpret_cast<int32_t*>(e->dImp),
                                                           reinterpret_cast<NodeDev*>(e->dImp + oNd),
@@ -1940,7 +2147,7 @@ int32_t dcsmc_reset_populations(dcsmc_engine* e) {
 
 int32_t dcsmc_population_release(dcsmc_engine* e, int32_t node) {
   if (!e) return DCSMC_EINVAL;
-  if (node < 0 || node >= e->nNodes || e->resident.empty()) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+  if (node < 0 || node >= e->nNodes || node >= (int)e->resident.size()) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   poolFree(e, node);
   return DCSMC_OK;
 }

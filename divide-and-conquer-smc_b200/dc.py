@@ -60,6 +60,7 @@ class DCOptions:
     # impl-1 output options (prototype/smc/DivideConquerMCAlgorithm.java:47,56); 0 = no summaries
     levelCutOffForOutput: int = 0
     useTransform: bool = True
+    retainSamples: bool = False  # keep the sample series behind the summaries (the reference's `samples` table)
 
     def engine_kwargs(self, device: int = 0) -> Dict[str, Any]:
         return dict(
@@ -72,7 +73,7 @@ class DCOptions:
             indexInCluster=self.indexInCluster, device=device, rngMode=self.rngMode,
             maxBetaAttempts=self.maxBetaAttempts, retainPopulations=1 if self.retainPopulations else 0,
             memoryBudgetBytes=self.memoryBudgetBytes, levelCutOffForOutput=int(self.levelCutOffForOutput),
-            useTransform=1 if self.useTransform else 0)
+            useTransform=1 if self.useTransform else 0, retainSamples=1 if self.retainSamples else 0)
 
 
 class ParticlePopulation:
@@ -258,8 +259,10 @@ class DefaultProcessorFactory(DCProcessorFactory):
 
         return _P()
 
+    writeFiles = True  # DistributedDC clears this on every rank but 0 of a sharded run
+
     def close(self):
-        if self.resultsFolder:
+        if self.resultsFolder and self.writeFiles:
             os.makedirs(self.resultsFolder, exist_ok=True)
             with open(os.path.join(self.resultsFolder, "timing.csv"), "w") as fh:
                 cols = ["node", "ESS", "rESS", "logZ", "nWorkers", "iterationProposalTime", "globalTime"]
@@ -281,11 +284,17 @@ class PosteriorSummaryProcessorFactory(DCProcessorFactory):
     resampled population (dcsmc_node_summary). The per-sample dump and the PDF histograms of the
     reference are not produced."""
 
-    def __init__(self, resultsFolder: Optional[str] = None):
+    writeFiles = True  # DistributedDC clears this on every rank but 0 of a sharded run
+
+    def __init__(self, resultsFolder: Optional[str] = None, samples: bool = False):
         self.resultsFolder = resultsFolder
         self.meanStats: List[Dict[str, Any]] = []
         self.varStats: List[Dict[str, Any]] = []
         self.deltaStats: List[Dict[str, Any]] = []
+        # the reference's `samples` table (logSamples, DivideConquerMCAlgorithm.java:508-519): (node, variable) -> the
+        # per-particle series; needs DCOptions.retainSamples. Rows are (node, variable, iteration, value).
+        self.wantSamples = samples
+        self.samples: Dict[tuple, np.ndarray] = {}
 
     def build(self, context: DCProcessorFactoryContext) -> DCProcessor:
         factory = self
@@ -300,13 +309,22 @@ class PosteriorSummaryProcessorFactory(DCProcessorFactory):
                     factory.varStats.append(dict(path=path, varMean=s["varMean"], varSD=s["varSD"]))
                 if s["hasDelta"]:
                     factory.deltaStats.append(dict(path=path, deltaMean=s["deltaMean"], deltaSD=s["deltaSD"]))
+                if factory.wantSamples:
+                    for variable, series in context.dc.nodeSamples(context.currentNode).items():
+                        factory.samples[(path if variable != "delta" else path, variable)] = series
 
         return _P()
 
     def close(self):
-        if not self.resultsFolder:
+        if not self.resultsFolder or not self.writeFiles:
             return
         os.makedirs(self.resultsFolder, exist_ok=True)
+        if self.wantSamples:
+            with open(os.path.join(self.resultsFolder, "samples.csv"), "w") as fh:
+                fh.write("node,variable,iteration,value\n")
+                for (path, variable), series in self.samples.items():
+                    for i, v in enumerate(series):
+                        fh.write(f"{path},{variable},{i},{float(v)!r}\n")
         for name, rows, cols in (("meanStats", self.meanStats, ["path", "meanMean", "meanSD"]),
                                  ("varStats", self.varStats, ["path", "varMean", "varSD"]),
                                  ("deltaStats", self.deltaStats, ["path", "deltaMean", "deltaSD"])):
@@ -374,7 +392,19 @@ class DistributedDC:
         if self._started:  # checkNotAlreadyStarted, DistributedDC.java:177-182
             raise RuntimeError()
         self._started = True
-        self.run()
+        # the one run of start() is profiled per launch, which yields the per-node iterationProposalTime of the
+        # `timing` rows (DefaultProcessorFactory.java:41-50); bench.py times run(), which is not
+        if self.engine is None:
+            self.engine = self._make_engine()
+        timed = hasattr(self.engine, "profile_enable") and hasattr(self.engine, "node_times")
+        if timed:
+            self.engine.profile_enable(True)
+        try:
+            self.run()
+        finally:
+            if timed:
+                self.engine.profile_enable(False)
+        self._nodeMs = self.engine.node_times() if timed else None
         self._finish()
 
     def run(self):
@@ -423,16 +453,18 @@ class DistributedDC:
                             self._xferBufs[child] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         plan, own = self.plan, self._nodeOwner
         e.reset_populations()
-        launches = updates = algbytes = nvbytes = 0
+        launches = updates = algbytes = nvbytes = h2d = d2h = 0
         devms = 0.0
 
         def account():
-            nonlocal launches, updates, algbytes, devms
+            nonlocal launches, updates, algbytes, devms, h2d, d2h
             info = e.run_info()
             launches += info.kernelLaunches
             updates += info.particleUpdates
             algbytes += info.algorithmicBytes
             devms += info.deviceMs
+            h2d += info.h2dBytes
+            d2h += info.d2hBytes
 
         mine = plan.my_tasks(rank)
         if mine:
@@ -472,7 +504,7 @@ class DistributedDC:
                     account()
         self.rootOwner = plan.node_owner[0]
         self.lastRun = dict(deviceMs=devms, kernelLaunches=launches, particleUpdates=updates, algorithmicBytes=algbytes,
-                            h2dBytes=0, d2hBytes=0, nvlinkBytes=nvbytes)
+                            h2dBytes=h2d, d2hBytes=d2h, nvlinkBytes=nvbytes)  # this rank's copies
 
     # -- population movement above the cut ----------------------------------------------------------
     def _transport(self, dist, dev) -> str:
@@ -490,36 +522,56 @@ class DistributedDC:
         # memory with POSIX shared memory and says so (hostPeerMemory)
         can = dev.type == "cuda" or getattr(self.engine, "hostPeerMemory", False)
         ok = 1 if (want == "p2p" and can and hasattr(self.engine, "peer_pool_handle")) else 0
+
+        def agree(v: int) -> int:  # every rank issues the same collectives whatever fails locally
+            flag = torch.tensor([v], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            return int(flag.item())
+
+        # step 1: the local handle (prepare() may fail to allocate the pool, cudaIpcGetMemHandle may be refused)
+        blk = None
         if ok:
             try:
-                self._exchange_pool_handles(dist, dev)
+                blk = self._pool_handle_block()
+            except Exception as ex:
+                self._p2pError = str(ex)
+                ok = 0
+        if agree(ok) == 1:
+            # step 2: all ranks have a handle -> one all-gather; step 3: map the peers, agree on the outcome
+            rank, world = dist.get_rank(), dist.get_world_size()
+            allb = torch.empty(world * blk.size, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allb, torch.from_numpy(blk).to(dev))
+            allb = allb.cpu().numpy().reshape(world, blk.size)
+            try:
+                self._peerGen = {}
+                for r in range(world):
+                    g, nbytes, handle = self._parse_handle_block(allb[r])
+                    self._peerGen[r] = g
+                    if r != rank:
+                        self.engine.peer_open(r, handle, g, nbytes)
             except Exception as ex:  # IPC refused (container policy, no peer access, ...)
                 self._p2pError = str(ex)
                 ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        self._transportChoice = "p2p" if int(flag.item()) == 1 else "nccl"
+            ok = agree(ok)
+        else:
+            ok = 0
+        self._transportChoice = "p2p" if ok == 1 else "nccl"
         return self._transportChoice
 
-    def _exchange_pool_handles(self, dist, dev):
-        """Every rank publishes (generation, IPC handle) of its pool; every rank maps all the others."""
-        import torch
-
-        rank, world = dist.get_rank(), dist.get_world_size()
-        handle, gen = self.engine.peer_pool_handle()
-        blk = np.zeros(8 + len(handle), np.uint8)
+    def _pool_handle_block(self) -> np.ndarray:
+        """(generation, pool bytes, IPC handle) of this engine's pool as one uint8 block."""
+        handle, gen, nbytes = self.engine.peer_pool_handle()
+        blk = np.zeros(16 + len(handle), np.uint8)
         blk[:8] = np.frombuffer(np.int64(gen).tobytes(), np.uint8)
-        blk[8:] = np.frombuffer(handle, np.uint8)
-        mine = torch.from_numpy(blk).to(dev)
-        allb = torch.empty(world * blk.size, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allb, mine)
-        allb = allb.cpu().numpy().reshape(world, blk.size)
-        self._peerGen = {}
-        for r in range(world):
-            g = int(np.frombuffer(allb[r, :8].tobytes(), np.int64)[0])
-            self._peerGen[r] = g
-            if r != rank:
-                self.engine.peer_open(r, allb[r, 8:].tobytes(), g)
+        blk[8:16] = np.frombuffer(np.int64(nbytes).tobytes(), np.uint8)
+        blk[16:] = np.frombuffer(handle, np.uint8)
+        return blk
+
+    @staticmethod
+    def _parse_handle_block(row: np.ndarray):
+        g = int(np.frombuffer(row[:8].tobytes(), np.int64)[0])
+        nbytes = int(np.frombuffer(row[8:16].tobytes(), np.int64)[0])
+        return g, nbytes, row[16:16 + F.IPC_HANDLE_BYTES].tobytes()
 
     def _top_levels_p2p(self, dist, dev, plan, rank, world, account) -> int:
         """Nodes above the cut, zero-copy: per level one small all-gather of export descriptors (which
@@ -545,11 +597,8 @@ class DistributedDC:
             self._p2pSync = torch.zeros(1, dtype=torch.int32, device=dev)
         # every block starts with (generation, IPC handle) of the sender's pool: a pool that was
         # re-allocated since the last exchange (new model, larger tree) is re-mapped on the fly
-        handle, gen = e.peer_pool_handle()
-        H = 8 + len(handle)
-        head = np.zeros(H, np.uint8)
-        head[:8] = np.frombuffer(np.int64(gen).tobytes(), np.uint8)
-        head[8:] = np.frombuffer(handle, np.uint8)
+        head = self._pool_handle_block()
+        H = head.size
         nvbytes = 0
         for lvl, (exp, width) in zip(plan.top_levels, self._p2pLevels):
             if width > 0:
@@ -565,9 +614,9 @@ class DistributedDC:
                 nodes, peers, descs = [], [], []
                 for child, src, dst in lvl.transfers:
                     if dst == rank:
-                        g = int(np.frombuffer(allb[src, :8].tobytes(), np.int64)[0])
+                        g, nb, hdl = self._parse_handle_block(allb[src, :H])
                         if self._peerGen.get(src) != g:
-                            e.peer_open(src, allb[src, 8:H].tobytes(), g)
+                            e.peer_open(src, hdl, g, nb)
                             self._peerGen[src] = g
                         k = exp[src].index(child)
                         nodes.append(child)
@@ -612,7 +661,9 @@ class DistributedDC:
         rank = dist.get_rank()
         own = self._nodeOwner
         keys = ["ess", "relEss", "logNormEstimate", "logScaling"]
-        mat = np.stack([np.where(own == rank, st[k], 0.0) for k in keys] + [np.where(own == rank, st["resampled"], 0).astype(np.float64)])
+        nodeMs = getattr(self, "_nodeMs", None)
+        mat = np.stack([np.where(own == rank, st[k], 0.0) for k in keys] + [np.where(own == rank, st["resampled"], 0).astype(np.float64)]
+                       + [np.where(own == rank, nodeMs if nodeMs is not None else 0.0, 0.0)])
         dev = torch.device("cuda", self.engine.options.device) if torch.cuda.is_available() else torch.device("cpu")
         tens = torch.from_numpy(mat).to(dev)
         dist.all_reduce(tens)
@@ -620,7 +671,33 @@ class DistributedDC:
         out = {k: mat[i] for i, k in enumerate(keys)}
         out["resampled"] = mat[4].astype(np.int32)
         out["done"] = np.ones(self.csr.nNodes, np.int32)
+        if nodeMs is not None:
+            self._nodeMs = mat[5]
         self._stats = out
+        return out
+
+    def nodeSamples(self, node) -> Dict[str, np.ndarray]:
+        """The `samples` rows of one node (logSamples, DivideConquerMCAlgorithm.java:508-519): naturalParam, meanSample,
+        varSample (internal nodes) of the node itself, and — when its parent reports deltas — the `delta` series the
+        reference logs under this node's path. Needs DCOptions.retainSamples; single-engine runs (the series live on the
+        rank that computed them)."""
+        i = self.csr.index[node] if not isinstance(node, (int, np.integer)) else int(node)
+        out: Dict[str, np.ndarray] = {}
+        cut = self.options.levelCutOffForOutput
+        depth = self.csr.depth()
+        if not self.options.retainSamples or cut <= 0 or self._dist() is not None:
+            return out
+        st = self.stats
+        e = self.engine
+        if depth[i] < cut and st["resampled"][i]:
+            out["naturalParam"] = e.node_samples(i, F.SAMPLE_NATURAL)
+            out["meanSample"] = e.node_samples(i, F.SAMPLE_MEAN)
+            if self.csr.nChildren(i) > 0:
+                out["varSample"] = e.node_samples(i, F.SAMPLE_VAR)
+        parent = int(self.csr.parent[i])
+        if parent >= 0 and depth[parent] + 1 < cut and st["resampled"][parent]:
+            kids = [int(c) for c in self.csr.children[self.csr.childOffsets[parent]:self.csr.childOffsets[parent + 1]]]
+            out["delta"] = e.node_samples(parent, F.SAMPLE_DELTA0 + kids.index(i))
         return out
 
     def nodeSummary(self, node) -> Dict[str, Any]:
@@ -675,14 +752,29 @@ class DistributedDC:
             out[i] = d
         return out
 
-    def _population_view(self, i: int, fetch=None) -> ParticlePopulation:
+    def _population_view(self, i: int, fetch=None, afterResampling: bool = False) -> ParticlePopulation:
+        """The population of node i before resampling (what DCProcessor.process gets first), or — afterResampling —
+        what its parent receives in `childrenPopulations` (DCRecursion.java:27-31: resample() ran if rESS was below
+        the threshold, so the weights are null and ESS = N)."""
         st = self.stats
+        if afterResampling and bool(st["resampled"][i]):
+            return ParticlePopulation(self.options.nParticles, float(st["logScaling"][i]), float(self.options.nParticles),
+                                      weights_null=True, fetch=fetch)
         return ParticlePopulation(self.options.nParticles, float(st["logScaling"][i]), float(st["ess"][i]),
                                   weights_null=False, fetch=fetch)
 
     def _finish(self):
         # DCProcessor.process sees the population BEFORE resampling (DCRecursion.java:27-28)
         csr = self.csr
+        dist0 = self._dist()
+        st0 = self.stats  # (a collective when sharded) also brings the per-node times of all ranks together
+        nodeMs = getattr(self, "_nodeMs", None)
+        if nodeMs is not None:
+            self.nodeTimeMs = {node: float(nodeMs[i]) for i, node in enumerate(csr.nodes)}
+        if dist0 is not None and dist0.get_rank() != 0:
+            for f in self.processorFactories:  # every rank runs the processors (their state is per process); rank 0 writes
+                if hasattr(f, "writeFiles"):
+                    f.writeFiles = False
         procs = []
         for i, node in enumerate(csr.nodes):
             ctx = DCProcessorFactoryContext(node, self.tree, self)
@@ -691,7 +783,7 @@ class DistributedDC:
         order = sorted(range(csr.nNodes), key=lambda i: (int(h[i]), i))
         for i in order:
             pop = self._population_view(i)
-            kids = [self._population_view(int(c)) for c in csr.children[csr.childOffsets[i]:csr.childOffsets[i + 1]]]
+            kids = [self._population_view(int(c), afterResampling=True) for c in csr.children[csr.childOffsets[i]:csr.childOffsets[i + 1]]]
             for p in procs[i]:
                 p.process(pop, kids)
         for f in self.processorFactories:

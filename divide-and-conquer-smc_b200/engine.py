@@ -141,6 +141,24 @@ class Engine:
         self._ck(self._L.dcsmc_node_summary(self._h, node, C.byref(s)))
         return s
 
+    def node_samples(self, node: int, which: int) -> np.ndarray:
+        """dcsmc_node_samples: one retained sample series of a summary node (F.SAMPLE_*)."""
+        out = np.empty(self.N)
+        self._ck(self._L.dcsmc_node_samples(self._h, node, which, _ptr(out, C.c_double)))
+        return out
+
+    def node_times(self) -> np.ndarray:
+        """dcsmc_node_times: per-node share of its level batch's device time (ms); profiled runs only."""
+        out = np.zeros(max(1, self.nNodes))
+        self._ck(self._L.dcsmc_node_times(self._h, _ptr(out, C.c_double)))
+        return out[:self.nNodes]
+
+    def population_view(self, node: int) -> F.PopulationView:
+        """dcsmc_population_view: borrowed device pointers (valid until the next run / reset / destroy)."""
+        v = F.PopulationView()
+        self._ck(self._L.dcsmc_population_view(self._h, node, C.byref(v)))
+        return v
+
     def all_node_stats(self) -> Dict[str, np.ndarray]:
         arr = (F.NodeStats * self.nNodes)()
         self._ck(self._L.dcsmc_all_node_stats(self._h, arr))
@@ -193,15 +211,15 @@ class Engine:
 
     # -- zero-copy sharing over NVLink peer memory (CUDA IPC) ---------------------------------------
     def peer_pool_handle(self):
-        """(64-byte IPC handle of this engine's pool, pool generation)"""
+        """(64-byte IPC handle of this engine's pool, pool generation, pool bytes)"""
         h = (C.c_char * F.IPC_HANDLE_BYTES)()
-        gen = C.c_int64()
-        self._ck(self._L.dcsmc_peer_pool_handle(self._h, h, C.byref(gen)))
-        return bytes(h), gen.value
+        gen, nbytes = C.c_int64(), C.c_int64()
+        self._ck(self._L.dcsmc_peer_pool_handle(self._h, h, C.byref(gen), C.byref(nbytes)))
+        return bytes(h), gen.value, nbytes.value
 
-    def peer_open(self, peer: int, handle: bytes, generation: int):
+    def peer_open(self, peer: int, handle: bytes, generation: int, poolBytes: int):
         buf = (C.c_char * F.IPC_HANDLE_BYTES).from_buffer_copy(handle)
-        self._ck(self._L.dcsmc_peer_open(self._h, peer, buf, generation))
+        self._ck(self._L.dcsmc_peer_open(self._h, peer, buf, generation, poolBytes))
 
     def export(self, nodes: Sequence[int]) -> bytes:
         r = np.ascontiguousarray(nodes, dtype=np.int32)

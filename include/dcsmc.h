@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DCSMC_ABI_VERSION 2
+#define DCSMC_ABI_VERSION 3
 
 enum {
   DCSMC_OK = 0,
@@ -86,10 +86,11 @@ typedef struct dcsmc_options {
   int32_t levelCutOffForOutput; /* DcSmcOptions.levelCutOffForOutput (prototype/smc/
                                    DivideConquerMCAlgorithm.java:56): posterior summaries for nodes
                                    with level() < this; 0 (default) = none, reference default 2 */
-  int64_t memoryBudgetBytes; /* 0: use 85% of free device memory */
+  int64_t memoryBudgetBytes; /* 0: use 80% of free device memory */
   int32_t useTransform;      /* MultiLevelModelOptions.useTransform (:47): summaries on the
                                 logistic scale (default 1) */
-  int32_t reserved1;
+  int32_t retainSamples;     /* 1: keep the per-particle sample series behind the summaries (the reference's
+                                `samples` table, DivideConquerMCAlgorithm.java:508-519) for dcsmc_node_samples */
 } dcsmc_options;
 
 typedef struct dcsmc_engine dcsmc_engine;
@@ -192,6 +193,40 @@ typedef struct dcsmc_node_summary_t {
 } dcsmc_node_summary_t;
 int32_t dcsmc_node_summary(dcsmc_engine* e, int32_t node, dcsmc_node_summary_t* out);
 
+/* The reference's `samples` table (logSamples, DivideConquerMCAlgorithm.java:508-519; rows node, variable,
+ * iteration, value): the per-particle series behind the summaries of a node with level() < levelCutOffForOutput,
+ * kept on the device when dcsmc_options.retainSamples = 1. `which`: DCSMC_SAMPLE_NATURAL ("naturalParam", :497),
+ * _MEAN ("meanSample", :499), _VAR ("varSample", internal nodes, :504), _DELTA0 + c ("delta" of child c, logged
+ * under the CHILD's path, :461). out[nParticles]. */
+enum { DCSMC_SAMPLE_NATURAL = 0, DCSMC_SAMPLE_MEAN = 1, DCSMC_SAMPLE_VAR = 2, DCSMC_SAMPLE_DELTA0 = 3 };
+int32_t dcsmc_node_samples(dcsmc_engine* e, int32_t node, int32_t which, double* out);
+
+/* DefaultProcessorFactory's iterationProposalTime (DefaultProcessorFactory.java:41-50): per node, the device
+ * time (ms) of the level batch it ran in divided by the sibling nodes of that batch. Filled by runs made with
+ * dcsmc_profile_enable(e, 1); zeros otherwise. out[nNodes]. */
+int32_t dcsmc_node_times(const dcsmc_engine* e, double* msPerNode);
+
+/* ParticlePopulation without a copy: BORROWED device pointers to the node's population, valid until the next
+ * run / reset / destroy on this engine (co-resident consumers: another CUDA library, a JNI direct buffer over
+ * device memory, a plotting kernel). Particle j of the population is row ancestors[j] of the columns when the
+ * node was resampled (ancestors != NULL), else row j with weight exp(logWeights[j] - maxLogWeight) / sumExp. */
+typedef struct dcsmc_population_view_t {
+  const double* state;        /* column c at state + c * stride; NULL for Markov / constant leaves */
+  const int32_t* istate;      /* Markov particle */
+  const double* logWeights;   /* raw log weights; NULL for leaves (all equal) */
+  const int32_t* ancestors;   /* NULL unless resampled on this engine */
+  int64_t stride;             /* elements between columns */
+  int32_t nParticles;
+  int32_t nColumns;           /* 6: mean, msgVar, logLik, descObs, descVar, variance; 2 (leaves): mean, descObs; 0 */
+  int32_t resampled;
+  int32_t onPeer;             /* the memory belongs to a peer engine's pool (mapped over NVLink) */
+  int32_t constantObservation; /* observed leaf that is not materialised: every particle is (observation, 0, 0, 0, 0, NaN) */
+  int32_t reserved;
+  double observation;
+  double logScaling, maxLogWeight, sumExp, ess;
+} dcsmc_population_view_t;
+int32_t dcsmc_population_view(dcsmc_engine* e, int32_t node, dcsmc_population_view_t* out);
+
 /* DistributedDC.getRootPopulation() / ParticlePopulation accessors (DistributedDC.java:107;
  * SURVEY §8a row P): copies the node's population AFTER the node step (resampled if
  * resampling ran) to host buffers; any pointer may be NULL.
@@ -237,15 +272,17 @@ int32_t dcsmc_reset_populations(dcsmc_engine* e);
  * resident (no release, no new run) until the consumer's run call has returned. */
 #define DCSMC_IPC_HANDLE_BYTES 64
 #define DCSMC_EXPORT_DESC_BYTES 128
-/* IPC handle of this engine's pool (allocates it if needed) and the pool's generation (changes
- * whenever the pool is re-allocated; peers must then re-open) */
-int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generation);
-/* map a peer engine's pool (no-op if that generation is already mapped) */
-int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64_t generation);
+/* IPC handle of this engine's pool (allocates it if needed), the pool's generation (changes
+ * whenever the pool is re-allocated; peers must then re-open) and its size in bytes */
+int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generation, int64_t* poolBytes);
+/* map a peer engine's pool (no-op if that generation is already mapped); poolBytes bounds every descriptor
+ * later imported from that peer */
+int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64_t generation, int64_t poolBytes);
 /* descriptors (n * DCSMC_EXPORT_DESC_BYTES host bytes) of finished, resident populations */
 int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* descs);
 /* install peer-resident populations as the finished populations of `nodes` (peers[k] = the id
- * given to dcsmc_peer_open for the owner of nodes[k]) */
+ * given to dcsmc_peer_open for the owner of nodes[k]). Every descriptor is validated before anything changes:
+ * same node, model, layout and nParticles, finished, and offset + size inside the mapped pool of that peer. */
 int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, const int32_t* peers,
                                      int32_t n, const void* descs);
 
@@ -281,7 +318,7 @@ enum {
   DCSMC_K_INTERNAL = 1, /* merge + propose + weight (DCRecursion.dcPropose) */
   DCSMC_K_SCAN = 2,     /* expNormalize + CDF + ESS partials */
   DCSMC_K_FINALIZE = 3, /* logScaling / ESS / resample decision per node */
-  DCSMC_K_DARTS = 4,    /* multinomial dart generation + bucket sort */
+  DCSMC_K_DARTS = 4,    /* multinomial: dart -> ancestor -> offspring count (no sort) */
   DCSMC_K_RESAMPLE = 5, /* ancestor search */
   DCSMC_K_GATHER = 6,   /* materialise a resampled population */
   DCSMC_K_MARKOV = 7,   /* Doc toy-model propose */

@@ -16,6 +16,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -274,21 +275,34 @@ static void descriptive(const double* x, int n, double* mean, double* sd) {
   *sd = n > 1 ? sqrt((accum - (accum2 * accum2 / n)) / (n - 1.0)) : 0.0;
 }
 
-int orc_node_summaries(int elemMode, int64_t seed, int32_t nodeId, int32_t N, int32_t maxAtt,
-                       int32_t useTransform, const double* injected, const double* mean,
-                       const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
-                       const double* childMean, const double* childVar, double* out) {
+/* series (optional): the per-particle sample series the reference logs to its `samples` table
+ * (logSamples, DivideConquerMCAlgorithm.java:508-519): [naturalParam][meanSample][varSample (internal nodes)]
+ * [delta of child 0 .. C-1 (if doDelta)], each N long. */
+static int node_summaries(int elemMode, int64_t seed, int32_t nodeId, int32_t N, int32_t maxAtt,
+                          int32_t useTransform, const double* injected, const double* mean,
+                          const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
+                          const double* childMean, const double* childVar, double* out, double* series) {
   double* buf = (double*)malloc(sizeof(double) * (size_t)N);
   if (!buf) return 1;
   const uint64_t G = 2 + (uint64_t)C;
+  int row = 0;
   /* printNodeStatistics :476-498 */
   for (int i = 0; i < N; ++i) {
     const double natural = summary_gauss(elemMode, seed, nodeId, injected, (uint64_t)i * G, maxAtt) * sqrt(msgVar[i]) + mean[i];
     buf[i] = summary_transform(elemMode, useTransform, natural);
+    if (series) {
+      series[i] = natural;
+      series[(size_t)N + i] = buf[i];
+    }
   }
+  row = 2;
   descriptive(buf, N, &out[0], &out[1]);
   out[2] = out[3] = 0.0;
-  if (variance) descriptive(variance, N, &out[2], &out[3]);
+  if (variance) {
+    descriptive(variance, N, &out[2], &out[3]);
+    if (series) memcpy(series + (size_t)row * N, variance, sizeof(double) * (size_t)N);
+    row++;
+  }
   /* printDeltaNodeStatistics :433-469 with sampleChildrenJointly :203-217 */
   for (int c = 0; doDelta && c < C; ++c) {
     for (int i = 0; i < N; ++i) {
@@ -300,9 +314,26 @@ int orc_node_summaries(int elemMode, int64_t seed, int32_t nodeId, int32_t N, in
       buf[i] = summary_transform(elemMode, useTransform, child) - summary_transform(elemMode, useTransform, root);
     }
     descriptive(buf, N, &out[4 + 2 * c], &out[5 + 2 * c]);
+    if (series) memcpy(series + (size_t)(row + c) * N, buf, sizeof(double) * (size_t)N);
   }
   free(buf);
   return 0;
+}
+
+int orc_node_summaries(int elemMode, int64_t seed, int32_t nodeId, int32_t N, int32_t maxAtt,
+                       int32_t useTransform, const double* injected, const double* mean,
+                       const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
+                       const double* childMean, const double* childVar, double* out) {
+  return node_summaries(elemMode, seed, nodeId, N, maxAtt, useTransform, injected, mean, msgVar, variance, C, doDelta,
+                        childMean, childVar, out, NULL);
+}
+
+int orc_node_sample_series(int elemMode, int64_t seed, int32_t nodeId, int32_t N, int32_t maxAtt,
+                           int32_t useTransform, const double* injected, const double* mean,
+                           const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
+                           const double* childMean, const double* childVar, double* out, double* series) {
+  return node_summaries(elemMode, seed, nodeId, N, maxAtt, useTransform, injected, mean, msgVar, variance, C, doDelta,
+                        childMean, childVar, out, series);
 }
 
 /* combine(List children, double variance), :18-41 */
@@ -770,26 +801,48 @@ static void initial_tasks(const orc_tree* t, int32_t node, int depth, int32_t* t
     initial_tasks(t, t->children[c], depth - 1, tasks, n);
 }
 
+/* The reference's executor (DistributedDC.java:221-224 + DCRecursionTask.prepareNextTask :77-93): the
+ * initial tasks run whole subtrees serially; a node above the cut becomes a task the moment its last child
+ * population is in the cluster map, and any free thread takes it. Nothing inside a node step is parallel. */
 typedef struct {
   orc_ctx* ctx;
-  int32_t* tasks;
-  int nTasks;
-  int next;
+  int32_t* ready;    /* FIFO of runnable nodes */
+  int head, tail;
+  int32_t* pending;  /* per node above the cut: children still missing */
+  char* isTask;      /* per node: an initial task (serial recursion through its subtree) */
+  int32_t* parent;
+  int remaining;     /* nodes still to finish (initial tasks + nodes above the cut) */
   pthread_mutex_t mu;
+  pthread_cond_t cv;
 } work_queue;
 
 static void* worker(void* arg) {
   work_queue* q = (work_queue*)arg;
   for (;;) {
     pthread_mutex_lock(&q->mu);
-    const int k = q->next < q->nTasks ? q->next++ : -1;
+    while (q->head == q->tail && q->remaining > 0) pthread_cond_wait(&q->cv, &q->mu);
+    if (q->remaining <= 0 && q->head == q->tail) {
+      pthread_mutex_unlock(&q->mu);
+      break;
+    }
+    const int32_t node = q->ready[q->head++];
     pthread_mutex_unlock(&q->mu);
-    if (k < 0) break;
     orc_ctx local = *q->ctx; /* error flag is per-thread; outputs are disjoint per node */
-    local.cache = NULL;
-    population* res = run_node(&local, q->tasks[k]);
-    q->ctx->cache[q->tasks[k]] = res;
+    population* res;
+    if (q->isTask[node]) {
+      local.cache = NULL; /* DCRecursionTask.run(node, false): recurse through the whole subtree */
+      res = run_node(&local, node);
+    } else {
+      res = run_node(&local, node); /* children are taken from the cache (getChildrenPopulationsFromCluster) */
+    }
+    pthread_mutex_lock(&q->mu);
+    q->ctx->cache[node] = res;
     if (local.error) q->ctx->error = local.error;
+    q->remaining--;
+    const int32_t par = q->parent[node];
+    if (par >= 0 && --q->pending[par] == 0) q->ready[q->tail++] = par;
+    pthread_cond_broadcast(&q->cv);
+    pthread_mutex_unlock(&q->mu);
   }
   return NULL;
 }
@@ -812,16 +865,45 @@ int orc_run(const orc_options* opt, const orc_tree* tree, const double* const* i
     /* nThreadsPerNode executor threads over the initial tasks (DistributedDC.java:221-224);
      * nothing inside a node step is parallel. */
     ctx.cache = (population**)calloc((size_t)tree->nNodes, sizeof(population*));
-    int32_t* tasks = (int32_t*)malloc(sizeof(int32_t) * (size_t)tree->nNodes);
+    const int32_t nN = tree->nNodes;
+    int32_t* tasks = (int32_t*)malloc(sizeof(int32_t) * (size_t)nN);
     int nTasks = 0;
     initial_tasks(tree, tree->root, opt->maximumDistributionDepth, tasks, &nTasks);
-    work_queue q = {&ctx, tasks, nTasks, 0, PTHREAD_MUTEX_INITIALIZER};
+    work_queue q;
+    q.ctx = &ctx;
+    q.ready = (int32_t*)malloc(sizeof(int32_t) * (size_t)nN);
+    q.head = q.tail = 0;
+    q.pending = (int32_t*)calloc((size_t)nN, sizeof(int32_t));
+    q.isTask = (char*)calloc((size_t)nN, 1);
+    q.parent = (int32_t*)malloc(sizeof(int32_t) * (size_t)nN);
+    for (int32_t n = 0; n < nN; ++n) q.parent[n] = -1;
+    for (int32_t n = 0; n < nN; ++n)
+      for (int c = tree->childOffsets[n]; c < tree->childOffsets[n + 1]; ++c) q.parent[tree->children[c]] = n;
+    q.parent[tree->root] = -1;
+    q.remaining = nTasks;
+    for (int k = 0; k < nTasks; ++k) {
+      q.isTask[tasks[k]] = 1;
+      q.ready[q.tail++] = tasks[k];
+    }
+    for (int k = 0; k < nTasks; ++k) /* nodes above the cut = proper ancestors of the tasks (below `root`) */
+      for (int32_t a = tasks[k] == tree->root ? -1 : q.parent[tasks[k]]; a >= 0 && q.pending[a] == 0; a = a == tree->root ? -1 : q.parent[a]) {
+        q.pending[a] = n_children(tree, a);
+        q.remaining++;
+      }
+    pthread_mutex_init(&q.mu, NULL);
+    pthread_cond_init(&q.cv, NULL);
     const int nt = opt->nThreads;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nt);
     for (int t = 0; t < nt; ++t) pthread_create(&th[t], NULL, worker, &q);
     for (int t = 0; t < nt; ++t) pthread_join(th[t], NULL);
+    pthread_mutex_destroy(&q.mu);
+    pthread_cond_destroy(&q.cv);
     free(th);
     free(tasks);
+    free(q.ready);
+    free(q.pending);
+    free(q.isTask);
+    free(q.parent);
   }
 
   population* rootPop = ctx.error ? NULL : run_node(&ctx, tree->root);

@@ -128,6 +128,13 @@ int orc_node_summaries(int elemMode, int64_t seed, int32_t nodeId, int32_t N, in
                        int32_t useTransform, const double* injected, const double* mean,
                        const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
                        const double* childMean, const double* childVar, double* out);
+/* same, and also the per-particle sample series the reference logs to its `samples` table (logSamples,
+ * DivideConquerMCAlgorithm.java:508-519): series = [naturalParam][meanSample][varSample (variance != NULL)]
+ * [delta of child 0..C-1 (doDelta)], each N long. */
+int orc_node_sample_series(int elemMode, int64_t seed, int32_t nodeId, int32_t N, int32_t maxAtt,
+                           int32_t useTransform, const double* injected, const double* mean,
+                           const double* msgVar, const double* variance, int32_t C, int32_t doDelta,
+                           const double* childMean, const double* childVar, double* out, double* series);
 int32_t orc_slots_per_particle(const orc_options* opt, const orc_tree* tree, int32_t node);
 
 #ifdef __cplusplus

@@ -120,6 +120,9 @@ def lib():
         L.orc_node_summaries.restype = C.c_int
         L.orc_node_summaries.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp,
                                          C.c_int32, C.c_int32, dp, dp, dp]
+        L.orc_node_sample_series.restype = C.c_int
+        L.orc_node_sample_series.argtypes = [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp,
+                                             C.c_int32, C.c_int32, dp, dp, dp, dp]
         L.orc_slots_per_particle.restype = C.c_int32
         L.orc_slots_per_particle.argtypes = [C.POINTER(OrcOptions), C.POINTER(OrcTree), C.c_int32]
         _lib = L
@@ -170,7 +173,10 @@ def run(
     prior: Optional[np.ndarray] = None,
     injected: Optional[List[Optional[np.ndarray]]] = None,
     dump: bool = False,
+    root: int = 0,
 ) -> OracleResult:
+    """`root` != 0 runs only the subtree under that node (DCRecursionTask.run(node, false)); the per-node outputs
+    of the other nodes stay zero and rootState/rootWeights describe that node's population."""
     L = lib()
     nN = csr.nNodes
     N = nParticles
@@ -197,7 +203,7 @@ def run(
     nt = arr(nTrials if nTrials is not None else np.zeros(nN, np.int32), np.int32)
     ns = arr(nSuccesses if nSuccesses is not None else np.zeros(nN, np.int32), np.int32)
     lo = arr(leafObs if leafObs is not None else np.zeros(nN, np.float64), np.float64)
-    tree = OrcTree(nN, 0, _p(off, C.c_int32), _p(ch, C.c_int32), _p(jh, C.c_int32), _p(lk, C.c_int32),
+    tree = OrcTree(nN, int(root), _p(off, C.c_int32), _p(ch, C.c_int32), _p(jh, C.c_int32), _p(lk, C.c_int32),
                    _p(nt, C.c_int32), _p(ns, C.c_int32), _p(lo, C.c_double))
     res = OracleResult(
         ess=np.zeros(nN), relEss=np.zeros(nN), logNormEstimate=np.zeros(nN), logScaling=np.zeros(nN),
@@ -265,13 +271,20 @@ def node_summaries(ref: OracleResult, csr, node: int, *, levelCutOffForOutput: i
         cv[k] = ref.state[ch][1][ci]
     out = np.zeros(4 + 2 * max(C_, 1))
     inj = None if injected is None else np.ascontiguousarray(injected, dtype=np.float64)
-    rc = L.orc_node_summaries(elemMode, masterRandomSeed, node, N, maxBetaAttempts, 1 if useTransform else 0,
-                              _p(inj, C.c_double), _p(mean, C.c_double), _p(msgVar, C.c_double),
-                              _p(variance, C.c_double), C_, doDelta, _p(cm, C.c_double), _p(cv, C.c_double),
-                              _p(out, C.c_double))
+    # the per-particle series behind the statistics = the reference's `samples` table (logSamples :508-519)
+    nSeries = 2 + (1 if C_ > 0 else 0) + (C_ if doDelta else 0)
+    series = np.zeros((nSeries, N))
+    rc = L.orc_node_sample_series(elemMode, masterRandomSeed, node, N, maxBetaAttempts, 1 if useTransform else 0,
+                                  _p(inj, C.c_double), _p(mean, C.c_double), _p(msgVar, C.c_double),
+                                  _p(variance, C.c_double), C_, doDelta, _p(cm, C.c_double), _p(cv, C.c_double),
+                                  _p(out, C.c_double), _p(series, C.c_double))
     assert rc == 0
-    res = dict(meanMean=out[0], meanSD=out[1], hasVar=C_ > 0, varMean=out[2], varSD=out[3], delta={})
+    res = dict(meanMean=out[0], meanSD=out[1], hasVar=C_ > 0, varMean=out[2], varSD=out[3], delta={},
+               samples=dict(naturalParam=series[0], meanSample=series[1]), deltaSamples={})
+    if C_ > 0:
+        res["samples"]["varSample"] = series[2]
     if doDelta:
         for k, ch in enumerate(kids):
             res["delta"][ch] = (out[4 + 2 * k], out[5 + 2 * k])
+            res["deltaSamples"][ch] = series[(3 if C_ > 0 else 2) + k]
     return res

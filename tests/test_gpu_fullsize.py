@@ -1,0 +1,140 @@
+"""GPU <-> oracle parity at the FULL sizes of BASELINE.json's configs (VERDICT r01 "next" 1b).
+
+Every per-node statistic (ESS, rESS, logNormEstimate, logScaling, resample flag) of the CUDA engine must
+equal the contract oracle's bit for bit (np.array_equal; tolerance 0 — the oracle runs the same fdlibm /
+exact-sum / Philox contract), and so must the root population that getRootPopulation()
+returns. The oracle is threaded exactly as the reference allows (independent subtrees below
+maximumDistributionDepth, DistributedDC.java:165-175), so each case finishes in seconds to a minute.
+
+  cfg2  NYS-shaped tree (3538 nodes), nParticles = 1e5, MULTINOMIAL, resample at every node — whole tree
+  cfg3  same tree, nParticles = 1e6 — three district subtrees through dcsmc_run_subtrees (the unit a rank of
+        the sharded run executes), incl. the 58-school district whose weight product N^-C underflows
+  cfg4  perfect binary tree depth 16 (131 071 nodes), observed Gaussian leaves, nParticles = 1e4 — whole tree
+  cfg5  shape root -> 3 -> 4 -> 4 binomial leaves at nParticles = 1e7, relativeEssThreshold = 0.5 (weighted
+        children, DCRecursion.java:29-31,59), both resampling schemes
+"""
+import os
+
+import numpy as np
+import pytest
+
+import dcsmc_b200 as d
+import oracle_lib as o
+from dcsmc_b200 import synth
+from dcsmc_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("resampled", "logScaling", "logNormEstimate", "ess", "relEss")
+CORES = os.cpu_count() or 1
+
+
+def dataset(rows):
+    ds = d.MultiLevelDataset(rows=rows)
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    return csr, nT, nS
+
+
+def host_memory_gib() -> float:
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
+
+
+def test_cfg2_whole_tree_1e5_particles_equals_oracle():
+    csr, nT, nS = dataset(synth.nys_shaped_rows())
+    N = 100_000
+    with Engine(nParticles=N) as e:  # defaults = the bench: MULTINOMIAL, threshold 1+1e-10, Philox seed 31
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        st = e.all_node_stats()
+        rs, _, rw = e.population(0)
+    ref = o.run(csr, N, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS,
+                nThreads=CORES, maximumDistributionDepth=2)
+    for k in KEYS:
+        assert np.array_equal(st[k], getattr(ref, k)), k
+    assert np.array_equal(rs, ref.rootState, equal_nan=True)
+    assert np.array_equal(rw, ref.rootWeights)
+    # the literal restatement of the Java order (sequential sums, libm): within BASELINE's 1e-9
+    lit = o.run(csr, N, rngMode=o.RNG_PHILOX, sumMode=o.SUM_JAVA, elemMode=o.ELEM_LIBM, nTrials=nT, nSuccesses=nS,
+                nThreads=CORES, maximumDistributionDepth=2)
+    assert np.allclose(st["logNormEstimate"], lit.logNormEstimate, rtol=1e-9, atol=1e-9)
+
+
+def test_cfg3_district_subtrees_1e6_particles_equal_oracle():
+    csr, nT, nS = dataset(synth.nys_shaped_rows())
+    N = 1_000_000
+    depth = csr.depth()
+    districts = [i for i in range(csr.nNodes) if depth[i] == 2]
+    byWidth = sorted(districts, key=lambda i: csr.nChildren(i))
+    picks = [byWidth[-1], byWidth[len(byWidth) // 3], byWidth[0]]  # widest (58 schools), a medium one, the narrowest
+    assert csr.nChildren(picks[0]) * np.log10(N) > 300, "the widest district must exercise the underflow path"
+    with Engine(nParticles=N) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run_subtrees(picks)
+        st = e.all_node_stats()
+        pops = {r: e.population(r) for r in picks}
+    sizes = csr.subtree_sizes()
+    for r in picks:
+        ref = o.run(csr, N, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS,
+                    nThreads=CORES, maximumDistributionDepth=1, root=r)
+        sub = np.flatnonzero(ref.ess != 0)
+        assert len(sub) == int(sizes[r])
+        for k in KEYS:
+            assert np.array_equal(st[k][sub], getattr(ref, k)[sub]), (r, k)
+        rs, _, rw = pops[r]
+        assert np.array_equal(rs, ref.rootState, equal_nan=True), r
+        assert np.array_equal(rw, ref.rootWeights), r
+
+
+def test_cfg4_binary_tree_depth16_1e4_particles_equals_oracle():
+    csr, leafKind, leafObs = synth.binary_gauss_tree(16)
+    assert csr.nNodes == 131071
+    N = 10_000
+    with Engine(nParticles=N) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(leafKind=leafKind, leafObs=leafObs)
+        e.run()
+        st = e.all_node_stats()
+        rs, _, rw = e.population(0)
+    ref = o.run(csr, N, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT, elemMode=o.ELEM_FDLIBM, leafKind=leafKind, leafObs=leafObs,
+                nThreads=CORES, maximumDistributionDepth=6)
+    for k in KEYS:
+        assert np.array_equal(st[k], getattr(ref, k)), k
+    assert np.array_equal(rs, ref.rootState, equal_nan=True)
+    assert np.array_equal(rw, ref.rootWeights)
+
+
+@pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
+def test_cfg5_shape_1e7_particles_ess_triggered_equals_oracle(scheme):
+    """nParticles = 1e7 (BASELINE config 5), ESS-triggered resampling: some internal nodes stay weighted, so
+    their parents take the per-particle weight product (DCRecursion.java:55-63)."""
+    need = 40.0  # GiB of host memory the threaded oracle may touch (12 subtree tasks x 5 populations x 0.64 GB)
+    avail = host_memory_gib()
+    threads = min(CORES, 12)
+    if avail and avail < need:
+        threads = max(1, int(threads * avail / need))
+    csr, nT, nS = dataset(synth.wide_rows(5, [3, 4, 4]))
+    assert csr.nNodes == 64
+    N = 10_000_000
+    with Engine(nParticles=N, resamplingScheme=scheme, relativeEssThreshold=0.5) as e:
+        e.set_tree(csr)
+        e.set_multilevel_model(nT, nS)
+        e.run()
+        st = e.all_node_stats()
+        rs, _, rw = e.population(0)
+    ref = o.run(csr, N, resamplingScheme=scheme, relativeEssThreshold=0.5, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, nThreads=threads, maximumDistributionDepth=2)
+    internal = [i for i in range(csr.nNodes) if csr.nChildren(i) > 0]
+    nRes = int(st["resampled"][internal].sum())
+    assert 0 < nRes < len(internal), "the case must mix resampled and weighted internal nodes"
+    for k in KEYS:
+        assert np.array_equal(st[k], getattr(ref, k)), k
+    assert np.array_equal(rs, ref.rootState, equal_nan=True)
+    assert np.array_equal(rw, ref.rootWeights)

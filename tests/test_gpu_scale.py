@@ -227,5 +227,5 @@ def test_engine_stream_timer_and_export_error_paths():
             e.export([1])  # consumed by its parent: not resident
         with pytest.raises(_ffi.DcsmcError):
             e.import_peer([1], [3], desc)  # peer 3 was never mapped with dcsmc_peer_open
-        handle, gen = e.peer_pool_handle()
-        assert len(handle) == _ffi.IPC_HANDLE_BYTES and gen >= 1
+        handle, gen, nbytes = e.peer_pool_handle()
+        assert len(handle) == _ffi.IPC_HANDLE_BYTES and gen >= 1 and nbytes == e.run_info().poolBytes

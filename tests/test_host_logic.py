@@ -22,7 +22,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/dcsmc.h but not exported"
     assert declared == set(_ffi.SYMBOLS)
-    assert L.dcsmc_abi_version() == 2
+    assert L.dcsmc_abi_version() == 3
 
 
 def test_options_default_mirror_dcoptions():
@@ -272,9 +272,10 @@ class FakePeerEngine(FakeEngine):
 
     def peer_pool_handle(self):
         name = self._shm.name.encode()
-        return name + b"\0" * (64 - len(name)), self.generation
+        return name + b"\0" * (64 - len(name)), self.generation, self.SLOT * self.nNodes
 
-    def peer_open(self, peer, handle, generation):
+    def peer_open(self, peer, handle, generation, poolBytes):
+        assert poolBytes == self.SLOT * self.nNodes
         from multiprocessing import shared_memory
 
         shm = shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode())
