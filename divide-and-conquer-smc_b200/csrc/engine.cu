@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -48,22 +49,38 @@ struct Plan {
   std::vector<int32_t> stepNodes;
 };
 
-// A plan made on an empty pool is a pure function of (tree, model, options, roots): cached together
-// with the pool state it leaves behind, so repeated runs skip planning and descriptor uploads.
+// A plan is a pure function of (tree, model, options, roots, pool state at entry): cached together with the pool
+// state it leaves behind, so repeated runs skip planning and descriptor uploads and replay a CUDA graph.
+// Plans made on an EMPTY pool (dcsmc_run, a rank's subtrees) store the whole per-node tables; CONTEXTUAL plans
+// (made with populations resident: the nodes above the cut of a sharded run, dcsmc_run_nodes) are keyed by the
+// entry state of the allocator and store only the nodes they touch.
+struct NodeDelta {
+  int node;
+  Slot slot;
+  char resident, imported;
+};
 struct CachedPlan {
   std::vector<int> roots;
   Plan plan;
+  bool contextual = false;
+  std::map<size_t, size_t> entryFree;  // contextual: free holes / top of the pool when the plan was made
+  size_t entryTop = 0;
+  uint64_t entryKids = 0;              // contextual: residency of the roots' children (decides what gets planned)
   std::map<size_t, size_t> freeBySize;
   size_t poolTop = 0;
   std::vector<Slot> slot;
   std::vector<char> resident, imported;
+  std::vector<NodeDelta> delta;        // contextual: state of every node the plan touched, after the plan
   std::vector<char> inPlan;  // per node: computed by this plan
   std::vector<int> finalResident;  // nodes still resident when the plan has run (its roots, unless retained)
+  int32_t* dStepNodes = nullptr;   // device copy of plan.stepNodes
+  bool onDevice = false;           // step list + descriptors of the plan's nodes are on the device, untouched since
   // the plan's whole launch sequence as a CUDA graph (captured on its first replay)
   mutable cudaGraphExec_t graphExec = nullptr;
   mutable uint64_t graphScratchGen = 0;
   mutable dcsmc_run_info graphInfo{};
 };
+constexpr size_t MAX_CACHED_PLANS = 24;
 
 }  // namespace
 
@@ -95,10 +112,10 @@ struct dcsmc_engine {
   // device tables
   NodeDev* dNodes = nullptr;
   NodeStats* dStats = nullptr;
+  int32_t* dErr = nullptr;           // device-side consistency flag of deferred imports (read at dcsmc_sync)
+  int32_t* hErr = nullptr;           // pinned
   LeafConst* dLeaf = nullptr;
   int32_t* dChildren = nullptr;
-  int32_t* dStepNodes = nullptr;     // step lists of the cached plan `devicePlan`
-  size_t stepNodesCap = 0;
   int32_t* dStepNodesTmp = nullptr;  // step lists of the current uncached plan
   size_t stepNodesTmpCap = 0;
   int32_t* curStepNodes = nullptr;   // the one the running plan uses
@@ -129,6 +146,7 @@ struct dcsmc_engine {
   std::vector<dcsmc_node_stats_t> hStats;
   std::vector<NodeStatsOut> hOut;   // per node: last fetched record (incl. m, S for exports)
   std::vector<int> statNodes;       // nodes whose hStats entry was written since the last reset
+  std::vector<int32_t> pendNodes;   // nodes of the last plan whose records still sit in hExport (flushStats)
   std::vector<int> externalNodes;   // nodes that got an external slot since the last reset
   struct PeerMap { char* base = nullptr; int64_t generation = -1; int64_t bytes = 0; };
   std::map<int, PeerMap> peers;     // peer engines' pools mapped through CUDA IPC
@@ -166,9 +184,14 @@ struct dcsmc_engine {
   size_t leafSmemSet[3] = {0, 0, 0};
   size_t smallSmemSet[3] = {0, 0, 0};
   size_t smallSmemSet512[3] = {0, 0, 0};
-  std::vector<CachedPlan> planCache;
-  const CachedPlan* devicePlan = nullptr;  // whose descriptors are currently uploaded
-  std::vector<int> descDirty;              // nodes whose device descriptor was rewritten since then
+  std::vector<std::unique_ptr<CachedPlan>> planCache;
+  // deferred mode (dcsmc_begin_deferred .. dcsmc_sync): run calls only enqueue; one host synchronisation at the end
+  bool deferred = false;
+  bool inFlight = false;           // statistics copies into hExport may still be running
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> callEvents;  // one timed pair per deferred call
+  size_t callEventsUsed = 0;
+  // device copies of small host arrays that repeat run after run (static schedule): keyed by content
+  std::map<std::string, char*> blobCache;
   char *dStage = nullptr, *hStage = nullptr;  // dcsmc_population_copy_to_host staging (device / pinned host)
   size_t stageCap = 0;
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
@@ -393,10 +416,47 @@ int ensureDevice(dcsmc_engine* e) {
 
 // (re)build the device-side tables that do not depend on the memory plan
 void clearPlanCache(dcsmc_engine* e) {
-  for (CachedPlan& cp : e->planCache)
-    if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec);
+  for (auto& cp : e->planCache) {
+    if (cp->graphExec) cudaGraphExecDestroy(cp->graphExec);
+    if (cp->dStepNodes) cudaFree(cp->dStepNodes);
+  }
   e->planCache.clear();
-  e->devicePlan = nullptr;
+  for (auto& kv : e->blobCache) cudaFree(kv.second);
+  e->blobCache.clear();
+}
+
+// the device descriptor of `node` was rewritten (by another plan, an unpack, an import): cached plans that
+// compute this node must upload their descriptors again before their next (graph) replay
+void descWritten(dcsmc_engine* e, int node, const CachedPlan* except) {
+  for (auto& cp : e->planCache)
+    if (cp.get() != except && cp->onDevice && cp->inPlan[node]) cp->onDevice = false;
+}
+void allDescWritten(dcsmc_engine* e, const CachedPlan* except) {
+  for (auto& cp : e->planCache)
+    if (cp.get() != except) cp->onDevice = false;
+}
+
+// device copy of a small host array whose content repeats run after run (node lists and descriptors of the
+// static schedule above the cut): uploaded once, found again by content
+int cachedBlob(dcsmc_engine* e, const void* data, size_t bytes, char** out) {
+  std::string key(static_cast<const char*>(data), bytes);
+  auto it = e->blobCache.find(key);
+  if (it != e->blobCache.end()) {
+    *out = it->second;
+    return DCSMC_OK;
+  }
+  if (e->blobCache.size() > 4096) {  // a caller whose lists never repeat: start over (after the device is done with them)
+    CK(cudaStreamSynchronize(e->stream));
+    for (auto& kv : e->blobCache) cudaFree(kv.second);
+    e->blobCache.clear();
+  }
+  char* d = nullptr;
+  CK(cudaMalloc((void**)&d, std::max<size_t>(bytes, 16)));
+  CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, e->stream));  // pageable source: staged before the call returns
+  e->pendingH2D += (int64_t)bytes;
+  e->blobCache.emplace(std::move(key), d);
+  *out = d;
+  return DCSMC_OK;
 }
 
 // per-leaf constants of the model (the per-run INPUT DATA: trial / success counts or observations). Staged in
@@ -476,6 +536,7 @@ int uploadTables(dcsmc_engine* e) {
   e->hNodes.assign(nN, NodeDev{});
   e->hStats.assign(nN, dcsmc_node_stats_t{});
   e->hOut.assign(nN, NodeStatsOut{});
+  e->pendNodes.clear();
   e->statNodes.clear();
   e->externalNodes.clear();
   for (Slot& sl : e->slot)  // buffers of unpacked populations (their size depends on the model)
@@ -484,9 +545,7 @@ int uploadTables(dcsmc_engine* e) {
   e->importFree.clear();
   e->slot.assign(nN, Slot{});
   e->poolNeed = 0;
-  e->descDirty.clear();
   clearPlanCache(e);
-  e->devicePlan = nullptr;
   e->resident.assign(nN, 0);
   e->imported.assign(nN, 0);
   e->freeBySize.clear();
@@ -1013,19 +1072,45 @@ int validateForRun(dcsmc_engine* e) {
       return e->fail(DCSMC_ECUDA, "pending CUDA error at %s: %s", label, cudaGetErrorString(_e)); \
   } while (0)
 
-// the device holds the step lists and node descriptors of this cached plan, untouched since
-bool descriptorsValid(const dcsmc_engine* e, const CachedPlan* cached) {
-  if (cached == nullptr || e->devicePlan != cached) return false;
-  // other plans / unpack may have rewritten descriptors since; they only matter if they hit this plan
-  for (int n : e->descDirty)
-    if (cached->inPlan[n]) return false;
-  return true;
+// scatter the statistics of the last plan from the staging buffer into hStats / hOut (see executePlan)
+void flushStats(const dcsmc_engine* ce) {
+  dcsmc_engine* e = const_cast<dcsmc_engine*>(ce);
+  if (e->pendNodes.empty()) return;
+  if (e->inFlight) {  // deferred calls: the copies into hExport are ordered on the stream
+    cudaSetDevice(e->opt.device);
+    cudaStreamSynchronize(e->stream);
+    e->inFlight = false;
+  }
+  for (size_t k = 0; k < e->pendNodes.size(); ++k) {
+    const NodeStatsOut& h = e->hExport[k];
+    const int n = e->pendNodes[k];
+    dcsmc_node_stats_t& o = e->hStats[n];
+    o.ess = h.ess;
+    o.relEss = h.relEss;
+    o.logNormEstimate = h.logZ;
+    o.logScaling = h.logScaling;
+    o.resampled = h.resampled == RES_WEIGHTED ? 0 : 1;
+    o.done = h.done;
+    e->hOut[n] = h;
+  }
+  e->statNodes.insert(e->statNodes.end(), e->pendNodes.begin(), e->pendNodes.end());
+  e->pendNodes.clear();
 }
 
-int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr) {
+double hostNowMs() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int executePlan(dcsmc_engine* e, Plan& plan, CachedPlan* cached = nullptr) {
   int rc;
   const int N = e->opt.nParticles;
+  static const bool hostProf = getenv("DCSMC_HOSTPROF") != nullptr;  // stderr: host milliseconds per phase of this call
+  const double tEntry = hostProf ? hostNowMs() : 0.0;
+  double tLaunched = 0.0, tSynced = 0.0;
   CKPOINT("executePlan entry");
+  // statistics of a previous plan of this session (dcsmc_run discards its predecessor's in
+  // dcsmc_reset_populations); deferred calls append to the staging buffer instead and are flushed after dcsmc_sync
+  if (!e->deferred) flushStats(e);
   // scratch sizing: CDF + look-back descriptors for internal steps, darts for multinomial
   size_t maxStep = 0, maxInternalStep = 0;
   for (auto& s : plan.steps) {
@@ -1063,18 +1148,28 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
     e->sampleSeriesTotal = total;
     CK(grow((void**)&e->dSumScratch, e->sumScratchCap, std::max<size_t>(1, total * (size_t)e->Npad), sizeof(double)));
   }
-  bool descriptorsOnDevice = descriptorsValid(e, cached);
-  if (cached != nullptr) e->descDirty.clear();
+  bool descriptorsOnDevice = cached != nullptr && cached->onDevice;
   {
-    int32_t*& buf = cached ? e->dStepNodes : e->dStepNodesTmp;
-    size_t& cap = cached ? e->stepNodesCap : e->stepNodesTmpCap;
-    if (plan.stepNodes.size() > cap) {
-      if (buf) cudaFree(buf);
-      buf = nullptr;
-      CK(cudaMalloc((void**)&buf, plan.stepNodes.size() * sizeof(int32_t)));
-      cap = plan.stepNodes.size();
-      descriptorsOnDevice = false;
-      e->scratchGen++;
+    int32_t* buf;
+    if (cached) {
+      if (cached->dStepNodes == nullptr) {
+        CK(cudaMalloc((void**)&cached->dStepNodes, std::max<size_t>(1, plan.stepNodes.size()) * sizeof(int32_t)));
+        descriptorsOnDevice = false;
+      }
+      buf = cached->dStepNodes;
+    } else {
+      if (plan.stepNodes.size() > e->stepNodesTmpCap) {
+        if (e->dStepNodesTmp) {
+          CK(cudaStreamSynchronize(e->stream));  // deferred calls may still read the old list
+          cudaFree(e->dStepNodesTmp);
+        }
+        e->dStepNodesTmp = nullptr;
+        CK(cudaMalloc((void**)&e->dStepNodesTmp, plan.stepNodes.size() * sizeof(int32_t)));
+        e->stepNodesTmpCap = plan.stepNodes.size();
+      } else if (e->deferred && e->inFlight) {
+        CK(cudaStreamSynchronize(e->stream));  // the one temporary list is about to be overwritten
+      }
+      buf = e->dStepNodesTmp;
     }
     e->curStepNodes = buf;
     if (!descriptorsOnDevice)
@@ -1083,27 +1178,40 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   }
   if (!descriptorsOnDevice) {
     // node descriptors for every node touched by the plan (a few nodes: one small copy each;
-    // otherwise the whole table)
+    // otherwise the whole table). Other cached plans that compute one of these nodes lose their claim.
     for (int n : plan.stepNodes) fillNodeDev(e, n);
     if (plan.stepNodes.size() * 16 < (size_t)e->nNodes) {
       for (int n : plan.stepNodes) {
         CK(cudaMemcpyAsync(e->dNodes + n, &e->hNodes[n], sizeof(NodeDev), cudaMemcpyHostToDevice, e->stream));
-        if (cached == nullptr) e->descDirty.push_back(n);
+        descWritten(e, n, cached);
       }
     } else {
-      if (cached == nullptr) e->devicePlan = nullptr;  // a large uncached plan: just re-upload next time
       CK(cudaMemcpyAsync(e->dNodes, e->hNodes.data(), sizeof(NodeDev) * e->nNodes, cudaMemcpyHostToDevice, e->stream));
+      allDescWritten(e, cached);
     }
-    if (cached != nullptr) e->devicePlan = cached;
+    if (cached != nullptr) cached->onDevice = true;
   }
   CKPOINT("descriptor upload");
   e->planStepNodes = plan.stepNodes.data();
   RunCtx c;
   makeCtx(e, c);
+  const dcsmc_run_info before = e->info;  // deferred calls accumulate into one record (dcsmc_begin_deferred zeroes it)
   e->info = dcsmc_run_info{};
   e->info.poolBytes = (int64_t)e->poolBytes;
-  e->info.h2dBytes = e->pendingH2D + (descriptorsOnDevice ? 0 : (int64_t)(plan.stepNodes.size() * sizeof(int32_t) + sizeof(NodeDev) * e->nNodes));
+  e->info.h2dBytes = e->pendingH2D + (descriptorsOnDevice ? 0 : (int64_t)(plan.stepNodes.size() * (sizeof(int32_t) + sizeof(NodeDev))));
   e->pendingH2D = 0;
+  cudaEvent_t evA = e->ev0, evB = e->ev1;
+  if (e->deferred) {
+    if (e->callEventsUsed == e->callEvents.size()) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&b));
+      e->callEvents.push_back({a, b});
+    }
+    evA = e->callEvents[e->callEventsUsed].first;
+    evB = e->callEvents[e->callEventsUsed].second;
+    e->callEventsUsed++;
+  }
   // level batches, each cut into chunks whose chains overlap the next chunk's propose kernel
   const bool overlap = !e->profile && e->overlapChunks > 1 && e->streamR != nullptr;
   auto launchAll = [&]() -> int {
@@ -1159,7 +1267,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   // captured once into a CUDA graph and replayed with one launch (no per-kernel launch gaps; this
   // matters for small populations and for the short per-GPU runs of a sharded tree).
   const bool useGraph = e->useGraphs && cached != nullptr && descriptorsOnDevice && !e->profile && !overlap;
-  CK(cudaEventRecord(e->ev0, e->stream));
+  CK(cudaEventRecord(evA, e->stream));
   if (useGraph) {
     if (cached->graphExec != nullptr && cached->graphScratchGen != e->scratchGen) {
       cudaGraphExecDestroy(cached->graphExec);
@@ -1193,42 +1301,55 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
   } else {
     if ((rc = launchAll())) return rc;
   }
-  CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaEventRecord(evB, e->stream));
   CKPOINT("level batches");
+  if (hostProf) tLaunched = hostNowMs();
   // fetch the statistics of the nodes this plan computed: compact records, pinned staging
   const size_t nPlan = plan.stepNodes.size();
-  if (nPlan > e->exportCap) {
+  const size_t off = e->pendNodes.size();  // 0 unless deferred calls are pending
+  if (off + nPlan > e->exportCap) {
+    const size_t want = std::max(off + nPlan, e->deferred ? (size_t)e->nNodes + 1024 : (size_t)0);
+    if (e->inFlight) CK(cudaStreamSynchronize(e->stream));
+    NodeStatsOut *nd = nullptr, *nh = nullptr;
+    CK(cudaMalloc((void**)&nd, want * sizeof(NodeStatsOut)));
+    CK(cudaMallocHost((void**)&nh, want * sizeof(NodeStatsOut)));
+    if (off) memcpy(nh, e->hExport, off * sizeof(NodeStatsOut));
     if (e->dExport) cudaFree(e->dExport);
     if (e->hExport) cudaFreeHost(e->hExport);
-    e->dExport = e->hExport = nullptr;
-    e->exportCap = 0;
-    CK(cudaMalloc((void**)&e->dExport, nPlan * sizeof(NodeStatsOut)));
-    CK(cudaMallocHost((void**)&e->hExport, nPlan * sizeof(NodeStatsOut)));
-    e->exportCap = nPlan;
+    e->dExport = nd;
+    e->hExport = nh;
+    e->exportCap = want;
   }
   if (nPlan > 0) {
-    k_export_stats<<<(unsigned)((nPlan + 255) / 256), 256, 0, e->stream>>>(e->dStats, e->curStepNodes, (int)nPlan, e->dExport);
+    k_export_stats<<<(unsigned)((nPlan + 255) / 256), 256, 0, e->stream>>>(e->dStats, e->curStepNodes, (int)nPlan, e->dExport + off,
+                                                                               e->dNodes, e->pool, (int32_t)e->poolGeneration);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->hExport, e->dExport, nPlan * sizeof(NodeStatsOut), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->hExport + off, e->dExport + off, nPlan * sizeof(NodeStatsOut), cudaMemcpyDeviceToHost, e->stream));
   }
   e->info.d2hBytes = (int64_t)(nPlan * sizeof(NodeStatsOut));
+  e->info.particleUpdates = e->info.nodesProcessed * (int64_t)N;
+  if (e->deferred) {
+    // no host synchronisation: the caller keeps enqueueing (the next level, a collective, the closing barrier)
+    e->inFlight = true;
+    e->pendNodes.insert(e->pendNodes.end(), plan.stepNodes.begin(), plan.stepNodes.end());
+    e->info.kernelLaunches += before.kernelLaunches;
+    e->info.particleUpdates += before.particleUpdates;
+    e->info.nodesProcessed += before.nodesProcessed;
+    e->info.algorithmicBytes += before.algorithmicBytes;
+    e->info.h2dBytes += before.h2dBytes;
+    e->info.d2hBytes += before.d2hBytes;
+    e->info.levelBatches += before.levelBatches;
+    e->curStep = -1;
+    return DCSMC_OK;
+  }
   CK(cudaStreamSynchronize(e->stream));
+  if (hostProf) tSynced = hostNowMs();
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->info.deviceMs = ms;
-  e->info.particleUpdates = e->info.nodesProcessed * (int64_t)N;
-  for (size_t k = 0; k < nPlan; ++k) {
-    const NodeStatsOut& h = e->hExport[k];
-    dcsmc_node_stats_t& o = e->hStats[plan.stepNodes[k]];
-    o.ess = h.ess;
-    o.relEss = h.relEss;
-    o.logNormEstimate = h.logZ;
-    o.logScaling = h.logScaling;
-    o.resampled = h.resampled == RES_WEIGHTED ? 0 : 1;
-    o.done = h.done;
-    e->hOut[plan.stepNodes[k]] = h;
-  }
-  e->statNodes.insert(e->statNodes.end(), plan.stepNodes.begin(), plan.stepNodes.end());
+  // the records stay in the pinned staging buffer; they are scattered into the per-node host tables when somebody
+  // asks (flushStats) — a loop of back-to-back runs on a 131 071-node tree spent 2 ms per run in that scatter
+  e->pendNodes.insert(e->pendNodes.end(), plan.stepNodes.begin(), plan.stepNodes.end());
   if (e->profile) {
     // per level batch: the device time of its launches, shared equally by the sibling nodes that ran in it
     // (what DefaultProcessorFactory reports as iterationProposalTime, DefaultProcessorFactory.java:41-50)
@@ -1249,6 +1370,9 @@ int executePlan(dcsmc_engine* e, Plan& plan, const CachedPlan* cached = nullptr)
         e->hNodeMs[plan.stepNodes[plan.steps[k].offset + j]] = stepMs[k] / std::max(1, plan.steps[k].count);
   }
   e->curStep = -1;
+  if (hostProf)
+    fprintf(stderr, "[dcsmc hostprof] plan %zu nodes: launch %.3f ms, wait %.3f ms, stats %.3f ms (device %.3f ms)\n",
+            plan.stepNodes.size(), tLaunched - tEntry, tSynced - tLaunched, hostNowMs() - tSynced, e->info.deviceMs);
   return DCSMC_OK;
 }
 
@@ -1263,6 +1387,17 @@ int prepare(dcsmc_engine* e) {
   return DCSMC_OK;
 }
 
+// residency of the roots' children: with the allocator state it decides what the planner does
+uint64_t kidsSignature(const dcsmc_engine* e, const std::vector<int>& roots) {
+  uint64_t h = 1469598103934665603ULL;
+  for (int r : roots)
+    for (int c = e->childOffsets[r]; c < e->childOffsets[r + 1]; ++c) {
+      h ^= (uint64_t)(uint32_t)e->children[c] * 2 + (e->resident[e->children[c]] ? 1 : 0);
+      h *= 1099511628211ULL;
+    }
+  return h;
+}
+
 int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
   int rc;
   if ((rc = prepare(e))) return rc;
@@ -1273,47 +1408,129 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
         emptyPool = false;
         break;
       }
-  if (emptyPool) {
-    for (CachedPlan& cp : e->planCache)
-      if (cp.roots == roots) {
-        e->freeBySize = cp.freeBySize;
-        e->poolTop = cp.poolTop;
-        if (descriptorsValid(e, &cp) && cp.finalResident.size() * 8 < (size_t)e->nNodes) {
-          // the device already holds this plan's descriptors and the pool is empty: only the nodes that
-          // stay resident need their host-side slot back (O(roots), not O(nNodes))
-          for (int n : cp.finalResident) {
-            e->slot[n] = cp.slot[n];
-            e->resident[n] = 1;
-          }
-        } else {
-          e->slot = cp.slot;
-          e->resident = cp.resident;
-          e->imported = cp.imported;
+  const uint64_t kids = emptyPool ? 0 : kidsSignature(e, roots);
+  for (auto& up : e->planCache) {
+    CachedPlan& cp = *up;
+    if (cp.roots != roots || cp.contextual == emptyPool) continue;
+    if (emptyPool) {
+      e->freeBySize = cp.freeBySize;
+      e->poolTop = cp.poolTop;
+      if (cp.onDevice && cp.finalResident.size() * 8 < (size_t)e->nNodes) {
+        // the device already holds this plan's descriptors and the pool is empty: only the nodes that
+        // stay resident need their host-side slot back (O(roots), not O(nNodes))
+        for (int n : cp.finalResident) {
+          e->slot[n] = cp.slot[n];
+          e->resident[n] = 1;
         }
-        return executePlan(e, cp.plan, &cp);
+      } else {
+        e->slot = cp.slot;
+        e->resident = cp.resident;
+        e->imported = cp.imported;
       }
+      return executePlan(e, cp.plan, &cp);
+    }
+    // contextual plan: valid when the allocator and the children are in the state it was made for (the schedule
+    // of a sharded run is static, so from the second run on this always holds)
+    if (cp.entryTop != e->poolTop || cp.entryKids != kids || cp.entryFree != e->freeBySize) continue;
+    for (const NodeDelta& d : cp.delta) {
+      const Slot& cur = e->slot[d.node];
+      if (cur.external && !cur.peer && cur.external != d.slot.external) e->importFree.push_back(cur.external);  // as poolFree would
+      e->slot[d.node] = d.slot;
+      e->resident[d.node] = d.resident;
+      e->imported[d.node] = d.imported;
+    }
+    e->freeBySize = cp.freeBySize;
+    e->poolTop = cp.poolTop;
+    return executePlan(e, cp.plan, &cp);
   }
   Plan plan;
-  if ((rc = planRoots(e, roots, plan))) return rc;
-  if (emptyPool && e->planCache.size() < 4) {
-    e->planCache.reserve(4);  // keeps &planCache[k] stable (devicePlan points into it)
-    CachedPlan cp;
-    cp.roots = roots;
-    cp.plan = plan;
-    cp.freeBySize = e->freeBySize;
-    cp.poolTop = e->poolTop;
-    cp.slot = e->slot;
-    cp.resident = e->resident;
-    cp.imported = e->imported;
-    cp.inPlan.assign(e->nNodes, 0);
-    for (int n : plan.stepNodes) {
-      cp.inPlan[n] = 1;
-      if (e->resident[n]) cp.finalResident.push_back(n);
+  const bool record = e->planCache.size() < MAX_CACHED_PLANS;
+  std::unique_ptr<CachedPlan> cp;
+  if (record) {
+    cp.reset(new CachedPlan());
+    cp->roots = roots;
+    cp->contextual = !emptyPool;
+    if (!emptyPool) {
+      cp->entryFree = e->freeBySize;
+      cp->entryTop = e->poolTop;
+      cp->entryKids = kids;
+      e->undo.clear();
+      e->undoOn = true;  // the log names every node the planner touches
     }
-    e->planCache.push_back(std::move(cp));
-    return executePlan(e, e->planCache.back().plan, &e->planCache.back());
   }
-  return executePlan(e, plan);
+  rc = planRoots(e, roots, plan);
+  std::vector<int> touched;
+  if (record && !emptyPool) {
+    for (const dcsmc_engine::Undo& u : e->undo) touched.push_back(u.node);
+    e->undo.clear();
+    e->undoOn = false;
+  }
+  if (rc) return rc;
+  if (!record) return executePlan(e, plan);
+  cp->plan = plan;
+  cp->freeBySize = e->freeBySize;
+  cp->poolTop = e->poolTop;
+  cp->inPlan.assign(e->nNodes, 0);
+  for (int n : plan.stepNodes) {
+    cp->inPlan[n] = 1;
+    if (e->resident[n]) cp->finalResident.push_back(n);
+  }
+  if (emptyPool) {
+    cp->slot = e->slot;
+    cp->resident = e->resident;
+    cp->imported = e->imported;
+  } else {
+    std::sort(touched.begin(), touched.end());
+    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+    for (int n : touched) cp->delta.push_back({n, e->slot[n], e->resident[n], e->imported[n]});
+  }
+  e->planCache.push_back(std::move(cp));
+  CachedPlan* held = e->planCache.back().get();
+  return executePlan(e, held->plan, held);
+}
+
+// Wire format of one exported population (DCSMC_EXPORT_DESC_BYTES host bytes).
+struct ExportDesc {
+  int32_t magic, N;
+  int64_t offset;       // of the population inside the owner's pool
+  int64_t generation;   // of that pool
+  double m, S, ess, relEss, logScaling, logZ;
+  int32_t resampled, done;
+  int64_t slotBytes;    // bytes of the population: offset + slotBytes must lie inside the owner's pool
+  int32_t model;        // DCSMC_MODEL_* — fixes the column layout together with `kind`
+  int32_t kind;         // KIND_* of the node on the owner (internal: 6 columns + logw; leaf: 2 columns)
+  int32_t node;         // node id on the owner (must equal the importing id: one tree, one numbering)
+  int32_t skipObs;      // the owner does not materialise observed leaves
+  char pad[DCSMC_EXPORT_DESC_BYTES - 104];
+};
+static_assert(sizeof(ExportDesc) == DCSMC_EXPORT_DESC_BYTES, "export descriptor size");
+
+// validation shared by the two import entry points (every descriptor, before any state changes)
+int validateImport(dcsmc_engine* e, const int32_t* nodes, const int32_t* peerIds, int32_t n, const ExportDesc* in,
+                   bool layoutOnly) {
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    const ExportDesc& d = in[k];
+    if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+    if (d.magic != PACK_MAGIC || d.N != e->opt.nParticles)
+      return e->fail(DCSMC_EINVAL, "exported population of node %d does not match this engine (magic/N)", node);
+    if (!(d.done == 1 || (layoutOnly && d.done == 2)))
+      return e->fail(DCSMC_EINVAL, "exported population of node %d is not finished (done = %d)", node, d.done);
+    if (d.node != node || d.model != e->model || d.kind != nodeKind(e, node) || d.skipObs != (skipObservedLeaves(e) ? 1 : 0))
+      return e->fail(DCSMC_EINVAL, "exported population of node %d has another layout (node %d, model %d, kind %d, skipObs %d)",
+                     node, d.node, d.model, d.kind, d.skipObs);
+    if (!layoutOnly && d.resampled != RES_WEIGHTED && d.resampled != RES_ANCESTORS && d.resampled != RES_MATERIALISED)
+      return e->fail(DCSMC_EINVAL, "exported population of node %d: bad resampling state %d", node, d.resampled);
+    auto it = e->peers.find(peerIds[k]);
+    if (it == e->peers.end() || !it->second.base || it->second.generation != d.generation)
+      return e->fail(DCSMC_ESTATE, "pool of peer %d (generation %lld) is not mapped: call dcsmc_peer_open", peerIds[k],
+                     (long long)d.generation);
+    if (d.slotBytes != (int64_t)slotBytes(e, node) || d.offset < 0 || d.offset % 256 != 0 ||
+        d.offset + d.slotBytes > it->second.bytes)
+      return e->fail(DCSMC_EINVAL, "exported population of node %d lies outside the pool of peer %d (offset %lld, %lld bytes, pool %lld)",
+                     node, peerIds[k], (long long)d.offset, (long long)d.slotBytes, (long long)it->second.bytes);
+  }
+  return DCSMC_OK;
 }
 
 }  // namespace
@@ -1422,6 +1639,8 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   chk("peer mappings");
   if (e->hImp) cudaFreeHost(e->hImp);
   if (e->dImp) cudaFree(e->dImp);
+  if (e->hErr) cudaFreeHost(e->hErr);
+  if (e->dErr) cudaFree(e->dErr);
   if (e->hLeafStage) cudaFreeHost(e->hLeafStage);
   chk("import staging");
   if (e->hExport) cudaFreeHost(e->hExport);
@@ -1438,7 +1657,7 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   chk("population staging (device)");
   if (e->dSumm) cudaFree(e->dSumm);
   if (e->dSumScratch) cudaFree(e->dSumScratch);
-  void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodes, e->dStepNodesTmp, e->dInj, e->dJavaState,
+  void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodesTmp, e->dInj, e->dJavaState,
                   e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1448,8 +1667,11 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->streamR) cudaStreamDestroy(e->streamR);
   for (cudaEvent_t ev : e->evPool) cudaEventDestroy(ev);
-  for (CachedPlan& cp : e->planCache)
-    if (cp.graphExec) cudaGraphExecDestroy(cp.graphExec);
+  clearPlanCache(e);
+  for (auto& pr : e->callEvents) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
   chk("streams, events, graphs");
   delete e;
   return DCSMC_OK;
@@ -1500,6 +1722,7 @@ int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root, const int3
   e->imported.clear();
   e->hStats.clear();
   e->hOut.clear();
+  e->pendNodes.clear();
   e->statNodes.clear();
   e->externalNodes.clear();
   e->freeBySize.clear();
@@ -1641,6 +1864,7 @@ int32_t dcsmc_run_nodes(dcsmc_engine* e, const int32_t* nodes, int32_t nNodes) {
 
 int32_t dcsmc_node_stats(const dcsmc_engine* e, int32_t node, dcsmc_node_stats_t* out) {
   if (!e || !out) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= (int)e->hStats.size()) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   *out = e->hStats[node];
   return DCSMC_OK;
@@ -1648,6 +1872,7 @@ int32_t dcsmc_node_stats(const dcsmc_engine* e, int32_t node, dcsmc_node_stats_t
 
 int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out) {
   if (!e || !out) return DCSMC_EINVAL;
+  flushStats(e);
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
   if ((int)e->hStats.size() != e->nNodes) {  // nothing computed on this engine yet: done == 0 everywhere
     memset(out, 0, sizeof(dcsmc_node_stats_t) * e->nNodes);
@@ -1659,6 +1884,7 @@ int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out) {
 
 int32_t dcsmc_node_summary(dcsmc_engine* e, int32_t node, dcsmc_node_summary_t* out) {
   if (!e || !out) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   memset(out, 0, sizeof *out);
   if (e->opt.levelCutOffForOutput <= 0 || e->dSumm == nullptr) return DCSMC_OK;
@@ -1681,6 +1907,7 @@ int32_t dcsmc_node_summary(dcsmc_engine* e, int32_t node, dcsmc_node_summary_t* 
 
 int32_t dcsmc_node_samples(dcsmc_engine* e, int32_t node, int32_t which, double* out) {
   if (!e || !out) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   if (!e->opt.retainSamples || e->opt.levelCutOffForOutput <= 0 || e->dSumScratch == nullptr ||
       (int)e->sampleBase.size() != e->nNodes || e->sampleBase[node] < 0)
@@ -1717,6 +1944,7 @@ int32_t dcsmc_node_times(const dcsmc_engine* e, double* msPerNode) {
 
 int32_t dcsmc_population_view(dcsmc_engine* e, int32_t node, dcsmc_population_view_t* out) {
   if (!e || !out) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
     return e->fail(DCSMC_ESTATE, "population of node %d is not resident (consumed by its parent, or not computed)", node);
@@ -1745,6 +1973,7 @@ int32_t dcsmc_population_view(dcsmc_engine* e, int32_t node, dcsmc_population_vi
 
 int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* state, int32_t* istate, double* weights) {
   if (!e) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
     return e->fail(DCSMC_ESTATE, "population of node %d is not resident (consumed by its parent, or not computed)", node);
@@ -1783,6 +2012,7 @@ int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* sta
 int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre, int32_t* istatePre,
                               double* logWeights, int32_t* ancestors) {
   if (!e) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
   if (!e->opt.retainPopulations) return e->fail(DCSMC_ESTATE, "dcsmc_debug_copy_node needs retainPopulations=1");
   if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
@@ -1878,6 +2108,7 @@ int64_t dcsmc_population_packed_bytes(const dcsmc_engine* e) {
 
 int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t node, void* deviceDst) {
   if (!e) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= e->nNodes || !deviceDst) return e->fail(DCSMC_EINVAL, "dcsmc_population_pack: bad arguments");
   if (node >= (int)e->resident.size() || node >= (int)e->hStats.size() || !e->resident[node] || !e->hStats[node].done)
     return e->fail(DCSMC_ESTATE, "population of node %d is not resident", node);
@@ -1894,6 +2125,7 @@ int32_t dcsmc_population_pack(dcsmc_engine* e, int32_t node, void* deviceDst) {
 
 int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* deviceSrc) {
   if (!e) return DCSMC_EINVAL;
+  flushStats(e);
   if (node < 0 || node >= e->nNodes || !deviceSrc) return e->fail(DCSMC_EINVAL, "dcsmc_population_unpack: bad arguments");
   int rc;
   if ((rc = prepare(e))) return rc;
@@ -1915,7 +2147,7 @@ int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* devic
   e->resident[node] = 1;
   e->imported[node] = 1;
   fillNodeDev(e, node);
-  e->descDirty.push_back(node);
+  descWritten(e, node, nullptr);
   CK(cudaMemcpyAsync(e->dNodes + node, &e->hNodes[node], sizeof(NodeDev), cudaMemcpyHostToDevice, e->stream));
   RunCtx c;
   makeCtx(e, c);
@@ -1935,21 +2167,6 @@ int32_t dcsmc_population_unpack(dcsmc_engine* e, int32_t node, const void* devic
 }
 
 // ---- zero-copy sharing over NVLink peer memory ---------------------------------------------------
-// Wire format of one exported population (DCSMC_EXPORT_DESC_BYTES host bytes).
-struct ExportDesc {
-  int32_t magic, N;
-  int64_t offset;       // of the population inside the owner's pool
-  int64_t generation;   // of that pool
-  double m, S, ess, relEss, logScaling, logZ;
-  int32_t resampled, done;
-  int64_t slotBytes;    // bytes of the population: offset + slotBytes must lie inside the owner's pool
-  int32_t model;        // DCSMC_MODEL_* — fixes the column layout together with `kind`
-  int32_t kind;         // KIND_* of the node on the owner (internal: 6 columns + logw; leaf: 2 columns)
-  int32_t node;         // node id on the owner (must equal the importing id: one tree, one numbering)
-  int32_t skipObs;      // the owner does not materialise observed leaves
-  char pad[DCSMC_EXPORT_DESC_BYTES - 104];
-};
-static_assert(sizeof(ExportDesc) == DCSMC_EXPORT_DESC_BYTES, "export descriptor size");
 
 int32_t dcsmc_peer_pool_handle(dcsmc_engine* e, void* handle, int64_t* generation, int64_t* poolBytes) {
   if (!e || !handle || !generation || !poolBytes) return DCSMC_EINVAL;
@@ -1988,6 +2205,7 @@ int32_t dcsmc_peer_open(dcsmc_engine* e, int32_t peer, const void* handle, int64
 
 int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* descs) {
   if (!e || n < 0 || (n > 0 && (!nodes || !descs))) return DCSMC_EINVAL;
+  flushStats(e);
   ExportDesc* out = static_cast<ExportDesc*>(descs);
   for (int k = 0; k < n; ++k) {
     const int node = nodes[k];
@@ -2025,33 +2243,14 @@ int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, cons
                                      const void* descs) {
   if (!e || n < 0 || (n > 0 && (!nodes || !peerIds || !descs))) return DCSMC_EINVAL;
   if (n == 0) return DCSMC_OK;
+  flushStats(e);
   int rc;
   if ((rc = prepare(e))) return rc;
   const ExportDesc* in = static_cast<const ExportDesc*>(descs);
   // pass 1: validate EVERY descriptor before any state changes — a descriptor is foreign input (another process
   // wrote it, a collective carried it): it must describe a finished population of the same model and layout
   // that lies inside the mapped pool of that peer
-  for (int k = 0; k < n; ++k) {
-    const int node = nodes[k];
-    const ExportDesc& d = in[k];
-    if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
-    if (d.magic != PACK_MAGIC || d.N != e->opt.nParticles)
-      return e->fail(DCSMC_EINVAL, "exported population of node %d does not match this engine (magic/N)", node);
-    if (!d.done) return e->fail(DCSMC_EINVAL, "exported population of node %d is not finished (done = 0)", node);
-    if (d.node != node || d.model != e->model || d.kind != nodeKind(e, node) || d.skipObs != (skipObservedLeaves(e) ? 1 : 0))
-      return e->fail(DCSMC_EINVAL, "exported population of node %d has another layout (node %d, model %d, kind %d, skipObs %d)",
-                     node, d.node, d.model, d.kind, d.skipObs);
-    if (d.resampled != RES_WEIGHTED && d.resampled != RES_ANCESTORS && d.resampled != RES_MATERIALISED)
-      return e->fail(DCSMC_EINVAL, "exported population of node %d: bad resampling state %d", node, d.resampled);
-    auto it = e->peers.find(peerIds[k]);
-    if (it == e->peers.end() || !it->second.base || it->second.generation != d.generation)
-      return e->fail(DCSMC_ESTATE, "pool of peer %d (generation %lld) is not mapped: call dcsmc_peer_open", peerIds[k],
-                     (long long)d.generation);
-    if (d.slotBytes != (int64_t)slotBytes(e, node) || d.offset < 0 || d.offset % 256 != 0 ||
-        d.offset + d.slotBytes > it->second.bytes)
-      return e->fail(DCSMC_EINVAL, "exported population of node %d lies outside the pool of peer %d (offset %lld, %lld bytes, pool %lld)",
-                     node, peerIds[k], (long long)d.offset, (long long)d.slotBytes, (long long)it->second.bytes);
-  }
+  if ((rc = validateImport(e, nodes, peerIds, n, in, false))) return rc;
   const size_t oNd = alignUp(sizeof(int32_t) * n, 256), oSt = oNd + alignUp(sizeof(NodeDev) * n, 256),
                total = oSt + alignUp(sizeof(NodeStats) * n, 256);
   // the pinned staging buffer is reused: the previous upload must have left it
@@ -2084,7 +2283,7 @@ int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, cons
     e->resident[node] = 1;
     e->imported[node] = 2;
     fillNodeDev(e, node);
-    e->descDirty.push_back(node);
+    descWritten(e, node, nullptr);
     hIds[k] = node;
     hNd[k] = e->hNodes[node];
     NodeStats z;
@@ -2120,8 +2319,173 @@ int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, cons
   return DCSMC_OK;  // stream order: the next run on this engine sees the imported descriptors
 }
 
+// ---- sharded runs without host round trips -------------------------------------------------------------
+int32_t dcsmc_stream(dcsmc_engine* e, void** stream) {
+  if (!e || !stream) return DCSMC_EINVAL;
+  *stream = (void*)e->stream;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_begin_deferred(dcsmc_engine* e) {
+  if (!e) return DCSMC_EINVAL;
+  if (e->profile) return e->fail(DCSMC_ESTATE, "deferred calls cannot be profiled per launch (dcsmc_profile_enable)");
+  int rc;
+  if ((rc = prepare(e))) return rc;
+  flushStats(e);
+  if (!e->dErr) {
+    CK(cudaMalloc((void**)&e->dErr, sizeof(int32_t)));
+    CK(cudaMallocHost((void**)&e->hErr, sizeof(int32_t)));
+  }
+  CK(cudaMemsetAsync(e->dErr, 0, sizeof(int32_t), e->stream));
+  e->deferred = true;
+  e->callEventsUsed = 0;
+  e->info = dcsmc_run_info{};
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_sync(dcsmc_engine* e) {
+  if (!e) return DCSMC_EINVAL;
+  if (!e->deferred) return e->fail(DCSMC_ESTATE, "dcsmc_sync without dcsmc_begin_deferred");
+  CK(cudaSetDevice(e->opt.device));
+  e->deferred = false;
+  *e->hErr = 0;
+  CK(cudaMemcpyAsync(e->hErr, e->dErr, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->inFlight = false;
+  if (*e->hErr != 0)
+    return e->fail(DCSMC_ESTATE, "deferred import of node %d: the owner's population is not where the cached layout "
+                                  "descriptor says (or not finished) — the static schedule changed; results of this run are invalid",
+                   *e->hErr - 1);
+  double total = 0.0;
+  for (size_t k = 0; k < e->callEventsUsed; ++k) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e->callEvents[k].first, e->callEvents[k].second));
+    total += ms;
+  }
+  e->callEventsUsed = 0;
+  e->info.deviceMs = total;
+  e->info.poolBytes = (int64_t)e->poolBytes;
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_stats_export_device(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* deviceDst) {
+  if (!e || n < 0 || (n > 0 && (!nodes || !deviceDst))) return DCSMC_EINVAL;
+  if (n == 0) return DCSMC_OK;
+  static_assert(sizeof(NodeStatsOut) == DCSMC_STATS_RECORD_BYTES, "statistics record size");
+  CK(cudaSetDevice(e->opt.device));
+  for (int k = 0; k < n; ++k)
+    if (nodes[k] < 0 || nodes[k] >= e->nNodes || nodes[k] >= (int)e->resident.size() || !e->resident[nodes[k]])
+      return e->fail(DCSMC_ESTATE, "population of node %d is not resident", nodes[k]);
+  char* dIds = nullptr;
+  int rc;
+  if ((rc = cachedBlob(e, nodes, sizeof(int32_t) * (size_t)n, &dIds))) return rc;
+  e->info.kernelLaunches++;
+  k_export_stats<<<(n + 127) / 128, 128, 0, e->stream>>>(e->dStats, reinterpret_cast<const int32_t*>(dIds), n,
+                                                        static_cast<NodeStatsOut*>(deviceDst), e->dNodes, e->pool,
+                                                        (int32_t)e->poolGeneration);
+  CK(cudaGetLastError());
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_population_export_layout(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* descs) {
+  if (!e || n < 0 || (n > 0 && (!nodes || !descs))) return DCSMC_EINVAL;
+  ExportDesc* out = static_cast<ExportDesc*>(descs);
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    if (node < 0 || node >= e->nNodes) return e->fail(DCSMC_EINVAL, "bad node %d", node);
+    if (node >= (int)e->resident.size() || !e->resident[node])
+      return e->fail(DCSMC_ESTATE, "population of node %d is not resident", node);
+    if (e->slot[node].external)
+      return e->fail(DCSMC_ESTATE, "node %d is itself an imported population; only pool residents can be exported", node);
+    ExportDesc d;
+    memset(&d, 0, sizeof d);
+    d.magic = PACK_MAGIC;
+    d.N = e->opt.nParticles;
+    d.offset = (int64_t)e->slot[node].offset;
+    d.generation = e->poolGeneration;
+    d.done = 2;  // layout only: the statistics travel on the device (dcsmc_stats_export_device)
+    d.slotBytes = (int64_t)e->slot[node].bytes;
+    d.model = e->model;
+    d.kind = nodeKind(e, node);
+    d.node = node;
+    d.skipObs = skipObservedLeaves(e) ? 1 : 0;
+    out[k] = d;
+  }
+  return DCSMC_OK;
+}
+
+
+int32_t dcsmc_population_import_peer_device(dcsmc_engine* e, const int32_t* nodes, const int32_t* peerIds, int32_t n,
+                                            const void* descs, const void* deviceStats, const int32_t* statIndex,
+                                            int32_t nRecords) {
+  if (!e || n < 0 || (n > 0 && (!nodes || !peerIds || !descs || !deviceStats || !statIndex))) return DCSMC_EINVAL;
+  if (n == 0) return DCSMC_OK;
+  int rc;
+  if ((rc = prepare(e))) return rc;
+  const ExportDesc* in = static_cast<const ExportDesc*>(descs);
+  if ((rc = validateImport(e, nodes, peerIds, n, in, true))) return rc;
+  for (int k = 0; k < n; ++k)
+    if (statIndex[k] < 0 || statIndex[k] >= nRecords) return e->fail(DCSMC_EINVAL, "statistics record %d out of range", statIndex[k]);
+  if (!e->deferred) return e->fail(DCSMC_ESTATE, "dcsmc_population_import_peer_device belongs between dcsmc_begin_deferred and dcsmc_sync");
+  // host bookkeeping + one blob [ids | NodeDev[] | statIdx] found again by content on every later run
+  const size_t oNd = alignUp(sizeof(int32_t) * n, 16), oIx = oNd + alignUp(sizeof(NodeDev) * n, 16),
+               oEx = oIx + alignUp(sizeof(int32_t) * n, 16), total = oEx + sizeof(int2) * n;
+  std::vector<char> blob(total, 0);
+  int32_t* hIds = reinterpret_cast<int32_t*>(blob.data());
+  NodeDev* hNd = reinterpret_cast<NodeDev*>(blob.data() + oNd);
+  int32_t* hIx = reinterpret_cast<int32_t*>(blob.data() + oIx);
+  int2* hEx = reinterpret_cast<int2*>(blob.data() + oEx);
+  for (int k = 0; k < n; ++k) {
+    const int node = nodes[k];
+    const dcsmc_engine::PeerMap& pm = e->peers[peerIds[k]];
+    poolFree(e, node);
+    Slot sl;
+    sl.external = pm.base + in[k].offset;
+    sl.peer = true;
+    e->slot[node] = sl;
+    e->externalNodes.push_back(node);
+    e->resident[node] = 1;
+    e->imported[node] = 2;
+    fillNodeDev(e, node);
+    descWritten(e, node, nullptr);
+    hIds[k] = node;
+    hNd[k] = e->hNodes[node];
+    hIx[k] = statIndex[k];
+    hEx[k] = make_int2((int32_t)(in[k].offset >> 8), (int32_t)in[k].generation);
+  }
+  char* dBlob = nullptr;
+  if ((rc = cachedBlob(e, blob.data(), total, &dBlob))) return rc;
+  // the imported statistics also go to the host's staging buffer (scattered into hStats when somebody asks)
+  const size_t off = e->pendNodes.size();
+  if (off + (size_t)n > e->exportCap) {
+    const size_t want = std::max<size_t>(off + (size_t)n, (size_t)e->nNodes + 1024);
+    if (e->inFlight) CK(cudaStreamSynchronize(e->stream));
+    NodeStatsOut *nd = nullptr, *nh = nullptr;
+    CK(cudaMalloc((void**)&nd, want * sizeof(NodeStatsOut)));
+    CK(cudaMallocHost((void**)&nh, want * sizeof(NodeStatsOut)));
+    if (off) memcpy(nh, e->hExport, off * sizeof(NodeStatsOut));
+    if (e->dExport) cudaFree(e->dExport);
+    if (e->hExport) cudaFreeHost(e->hExport);
+    e->dExport = nd;
+    e->hExport = nh;
+    e->exportCap = want;
+  }
+  e->info.kernelLaunches++;
+  k_scatter_import_dev<<<(n + 127) / 128, 128, 0, e->stream>>>(
+      e->dNodes, e->dStats, reinterpret_cast<const int32_t*>(dBlob), reinterpret_cast<const NodeDev*>(dBlob + oNd),
+      reinterpret_cast<const int32_t*>(dBlob + oIx), reinterpret_cast<const int2*>(dBlob + oEx),
+      static_cast<const NodeStatsOut*>(deviceStats), n, e->dExport + off, e->dErr);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->hExport + off, e->dExport + off, (size_t)n * sizeof(NodeStatsOut), cudaMemcpyDeviceToHost, e->stream));
+  e->inFlight = true;
+  e->pendNodes.insert(e->pendNodes.end(), nodes, nodes + n);
+  e->statNodes.insert(e->statNodes.end(), nodes, nodes + n);
+  return DCSMC_OK;
+}
+
 int32_t dcsmc_reset_populations(dcsmc_engine* e) {
   if (!e) return DCSMC_EINVAL;
+  e->pendNodes.clear();  // statistics nobody asked for
   // O(nodes touched since the last reset), not O(nNodes): a rank of a sharded run only ever touches
   // its own part of a large tree
   for (int n : e->externalNodes)

@@ -233,6 +233,39 @@ class Engine:
         buf = (C.c_char * max(1, len(descs))).from_buffer_copy(descs if descs else b"\0")
         self._ck(self._L.dcsmc_population_import_peer(self._h, _ptr(r, C.c_int32), _ptr(q, C.c_int32), len(r), buf))
 
+    # -- sharded runs without host round trips (include/dcsmc.h) ----------------------------------------
+    def stream(self) -> int:
+        """the engine's launching stream (cudaStream_t as an integer)"""
+        p = C.c_void_p()
+        self._ck(self._L.dcsmc_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def begin_deferred(self):
+        self._ck(self._L.dcsmc_begin_deferred(self._h))
+
+    def sync(self):
+        self._ck(self._L.dcsmc_sync(self._h))
+
+    def stats_export_device(self, nodes: Sequence[int], device_ptr: int):
+        r = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._ck(self._L.dcsmc_stats_export_device(self._h, _ptr(r, C.c_int32), len(r), C.c_void_p(device_ptr)))
+
+    def export_layout(self, nodes: Sequence[int]) -> bytes:
+        r = np.ascontiguousarray(nodes, dtype=np.int32)
+        out = (C.c_char * (F.EXPORT_DESC_BYTES * max(1, len(r))))()
+        self._ck(self._L.dcsmc_population_export_layout(self._h, _ptr(r, C.c_int32), len(r), out))
+        return bytes(out)[:F.EXPORT_DESC_BYTES * len(r)]
+
+    def import_peer_device(self, nodes: Sequence[int], peers: Sequence[int], descs: bytes, device_stats_ptr: int,
+                           stat_index: Sequence[int], n_records: int):
+        r = np.ascontiguousarray(nodes, dtype=np.int32)
+        q = np.ascontiguousarray(peers, dtype=np.int32)
+        ix = np.ascontiguousarray(stat_index, dtype=np.int32)
+        buf = (C.c_char * max(1, len(descs))).from_buffer_copy(descs if descs else b"\0")
+        self._ck(self._L.dcsmc_population_import_peer_device(
+            self._h, _ptr(r, C.c_int32), _ptr(q, C.c_int32), len(r), buf, C.c_void_p(device_stats_ptr), _ptr(ix, C.c_int32),
+            int(n_records)))
+
     def reset_populations(self):
         self._ck(self._L.dcsmc_reset_populations(self._h))
 

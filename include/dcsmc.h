@@ -286,6 +286,33 @@ int32_t dcsmc_population_export(dcsmc_engine* e, const int32_t* nodes, int32_t n
 int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, const int32_t* peers,
                                      int32_t n, const void* descs);
 
+/* ---- sharded runs without host round trips ---------------------------------------------------
+ * The schedule above the cut is static (same tree, same plan, same pool offsets every run), so from the second run on
+ * nothing but the 64-byte statistics of the exported populations has to move between ranks, and it can move on
+ * the device: producers publish the records (dcsmc_stats_export_device) into a device buffer, ONE small
+ * all-gather ordered on the engine's stream (dcsmc_stream; NCCL or any stream-ordered transport) carries them —
+ * and is the "producers are done" barrier —, consumers install them with the cached layout descriptors
+ * (dcsmc_population_import_peer_device). Between dcsmc_begin_deferred and dcsmc_sync the run calls only
+ * enqueue work: the host synchronises once per run, not once per level (DCRecursionTask.java:77-93,108-115 is
+ * the reference's per-node hand-over through the cluster map). */
+#define DCSMC_STATS_RECORD_BYTES 64
+/* the engine's launching stream (a cudaStream_t): order collectives after / before the engine's kernels on it */
+int32_t dcsmc_stream(dcsmc_engine* e, void** cudaStream);
+/* run calls (dcsmc_run_subtrees, dcsmc_run_nodes) return after enqueueing; statistics and dcsmc_last_run_info
+ * (accumulated over the calls) become valid at dcsmc_sync */
+int32_t dcsmc_begin_deferred(dcsmc_engine* e);
+int32_t dcsmc_sync(dcsmc_engine* e);
+/* write the statistics records (DCSMC_STATS_RECORD_BYTES each) of resident `nodes` into a DEVICE buffer, in order */
+int32_t dcsmc_stats_export_device(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* deviceDst);
+/* descriptors (n * DCSMC_EXPORT_DESC_BYTES host bytes) of resident populations WITHOUT their statistics: where the
+ * population lies in this engine's pool. Host bookkeeping only — valid while the populations are still being computed. */
+int32_t dcsmc_population_export_layout(dcsmc_engine* e, const int32_t* nodes, int32_t n, void* descs);
+/* dcsmc_population_import_peer with the statistics of nodes[k] read on the device: record statIndex[k] of the
+ * DEVICE buffer deviceStats (nRecords records, e.g. the all-gathered exports of every rank). Same validation. */
+int32_t dcsmc_population_import_peer_device(dcsmc_engine* e, const int32_t* nodes, const int32_t* peers, int32_t n,
+                                            const void* descs, const void* deviceStats, const int32_t* statIndex,
+                                            int32_t nRecords);
+
 /* ---- planning without a device ---------------------------------------------------------
  * The schedule and the memory plan are a pure function of (options, tree, leaf kinds, pool size): this
  * entry point runs the planner on the host only — no CUDA device is needed or touched — and reports what

@@ -37,6 +37,21 @@ def main():
                 root = None
                 if rank == ddc.rootOwner:
                     root = ddc.getRootPopulation().particles.copy()
+                # runs 2..4 replay the static schedule without host round trips (deferred calls, statistics exchanged
+                # on the device, cached + graphed plans above the cut): same bits as the first, host-synchronised run
+                def same_as_first(tag):
+                    again = ddc.stats
+                    for k in ("ess", "relEss", "logNormEstimate", "logScaling", "resampled"):
+                        assert np.array_equal(sharded[k], again[k]), (scheme, thr, depth, k, tag)
+                    if root is not None:
+                        s_, _, _ = ddc.engine.population(0)
+                        assert np.array_equal(root, s_, equal_nan=True), (scheme, thr, depth, tag)
+
+                for rep in range(3):
+                    ddc.run()
+                    same_as_first(f"replay {rep}")
+                if os.environ.get("DCSMC_TRANSPORT", "p2p") == "p2p" and ddc._transportChoice == "p2p":
+                    assert getattr(ddc, "_p2pStatic", None) is not None and ddc._p2pBufs is not None, "the fast path did not run"
                 # single-GPU run on every rank (no process group use): engine.run()
                 ddc.engine.run()
                 single = ddc.engine.all_node_stats()
@@ -45,6 +60,9 @@ def main():
                 if root is not None:
                     s, _, _ = ddc.engine.population(0)
                     assert np.array_equal(root, s, equal_nan=True)
+                # and the sharded schedule again after another plan used the engine (descriptor invalidation)
+                ddc.run()
+                same_as_first("after the single-GPU run")
                 tot = torch.tensor([moved], device="cuda", dtype=torch.float64)
                 dist.all_reduce(tot)
                 assert tot.item() > 0, "nothing crossed NVLink"

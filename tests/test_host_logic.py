@@ -237,6 +237,7 @@ class FakePeerEngine(FakeEngine):
         self._peers = {}
         self._remote = {}
         self.generation = 1
+        self._deferred = False
 
     # pool-resident populations: self.pop[n] is a view into the shared pool
     def _compute(self, n):
@@ -300,6 +301,40 @@ class FakePeerEngine(FakeEngine):
         st = super().all_node_stats()
         return st
 
+    # ---- the host-sync-free schedule of runs 2.. (DistributedDC._top_levels_fast): same entry points as the CUDA
+    # engine; "device" buffers are CPU tensors here, a statistics record is 8 doubles: node, generation, slot, 0...
+    fastCalls = 0
+
+    def stream(self):
+        return 0
+
+    def begin_deferred(self):
+        self._deferred = True
+
+    def sync(self):
+        assert self._deferred
+        self._deferred = False
+
+    def stats_export_device(self, nodes, ptr):
+        assert self._deferred
+        rec = np.zeros((len(nodes), 8))
+        for k, n in enumerate(nodes):
+            assert n in self.pop, f"node {n} is not resident"
+            rec[k, :3] = (n, self.generation, n)
+        C.memmove(ptr, rec.ctypes.data, rec.nbytes)
+
+    def import_peer_device(self, nodes, peers, descs, ptr, index, nRecords):
+        assert self._deferred
+        rec = np.empty((nRecords, 8))
+        C.memmove(rec.ctypes.data, ptr, rec.nbytes)
+        for k, (n, p_) in enumerate(zip(nodes, peers)):
+            d_ = np.frombuffer(descs[k * 128:(k + 1) * 128], np.int64)
+            r = rec[index[k]]
+            # the published record must describe the population the cached descriptor points at
+            assert int(r[0]) == n and int(r[1]) == int(d_[1]) == self._peers[p_][2] and int(r[2]) == int(d_[0]), (n, r, d_)
+            self._remote[n] = self._peers[p_][1][int(d_[0])]
+        FakePeerEngine.fastCalls += 1
+
     def close(self):
         for shm, _, _ in self._peers.values():
             shm.close()
@@ -329,6 +364,9 @@ def _gloo_worker_p2p(rank, world, port, depth_opt, q):
                 vals.append(float(ddc.engine.pop[0].sum()))
         vals = vals or [None]
         final = float(ddc.stats["logScaling"][0])
+        # runs 2 and 3 took the schedule without host round trips (a rank that imports nothing makes no fast call)
+        imports = any(lv["imports"] is not None for lv in ddc._p2pStatic)
+        assert ddc._p2pStatic is not None and (FakePeerEngine.fastCalls > 0) == imports
         q.put((rank, vals, final, ddc._transportChoice, ddc.lastRun["nvlinkBytes"]))
         dist.barrier()
         ddc.engine.close()
