@@ -109,7 +109,7 @@ SYMBOLS = [
     "dcsmc_timer_begin", "dcsmc_timer_end",
     "dcsmc_node_samples", "dcsmc_node_times", "dcsmc_population_view",
     "dcsmc_stream", "dcsmc_begin_deferred", "dcsmc_sync", "dcsmc_stats_export_device", "dcsmc_population_export_layout",
-    "dcsmc_population_import_peer_device",
+    "dcsmc_population_import_peer_device", "dcsmc_stats_matrix_device",
     "dcsmc_node_summary", "dcsmc_plan_query", "dcsmc_host_eval", "dcsmc_peer_pool_handle", "dcsmc_peer_open", "dcsmc_population_export", "dcsmc_population_import_peer",
 ]
 IPC_HANDLE_BYTES, EXPORT_DESC_BYTES, STATS_RECORD_BYTES = 64, 128, 64
@@ -167,6 +167,7 @@ def lib():
     L.dcsmc_stream.argtypes = [vp, P(vp)]
     L.dcsmc_begin_deferred.argtypes = [vp]
     L.dcsmc_sync.argtypes = [vp]
+    L.dcsmc_stats_matrix_device.argtypes = [vp, vp]
     L.dcsmc_stats_export_device.argtypes = [vp, P(i32), i32, vp]
     L.dcsmc_population_export_layout.argtypes = [vp, P(i32), i32, vp]
     L.dcsmc_population_import_peer_device.argtypes = [vp, P(i32), P(i32), i32, vp, vp, P(i32), i32]

@@ -99,7 +99,8 @@ struct dcsmc_engine {
 
   // topology / model (host)
   int nNodes = 0, root = 0;
-  std::vector<int32_t> childOffsets, children, parent, height, javaHash;
+  std::vector<int32_t> childOffsets, children, parent, height, javaHash, subtreeSize;
+  bool preorder = false;  // nodes are numbered in pre-order (subtree of r = ids [r, r + subtreeSize[r]))
   int model = -1;
   std::vector<int32_t> leafKind, nTrials, nSuccesses;
   std::vector<double> leafObs;
@@ -124,7 +125,11 @@ struct dcsmc_engine {
   uint64_t* dJavaState = nullptr;
   double *dMarkovT = nullptr, *dMarkovPrior = nullptr;
   bool tablesDirty = true;
-  bool leafDirty = false;  // only the leaf data changed (same tree, same leaf kinds): re-upload dLeaf, keep plans
+  // the leaf data (trial / success counts, observations) is the per-run INPUT: a new set on the same tree and leaf
+  // kinds bumps leafVersion; a plan uploads the entries of the leaves it reads (its subtrees' id ranges) when its
+  // own copy is older — a rank of a sharded run never touches the other ranks' leaves
+  uint64_t leafVersion = 1, leafFullVersion = 0;
+  std::vector<uint64_t> leafVer;  // per node: version of its entry on the device
   size_t tableNodesCap = 0, tableEdgesCap = 0;  // sizes the device tables were allocated for
 
   // population pool
@@ -459,9 +464,10 @@ int cachedBlob(dcsmc_engine* e, const void* data, size_t bytes, char** out) {
   return DCSMC_OK;
 }
 
-// per-leaf constants of the model (the per-run INPUT DATA: trial / success counts or observations). Staged in
-// pinned memory so the copy is asynchronous; the previous copy has completed (every run ends with a sync).
-int uploadLeafTable(dcsmc_engine* e) {
+// per-leaf constants of the model (the per-run INPUT DATA: trial / success counts or observations) for the nodes
+// [lo, hi). Staged in pinned memory (entry n at offset n, so ranges never overlap); a previous copy out of the
+// same entries has completed (every run ends with a sync).
+int uploadLeafRange(dcsmc_engine* e, int lo, int hi) {
   const int nN = e->nNodes;
   if ((size_t)nN > e->leafStageCap) {
     if (e->hLeafStage) cudaFreeHost(e->hLeafStage);
@@ -470,19 +476,48 @@ int uploadLeafTable(dcsmc_engine* e) {
     CK(cudaMallocHost((void**)&e->hLeafStage, sizeof(LeafConst) * (size_t)nN));
     e->leafStageCap = (size_t)nN;
   }
+  if ((int)e->leafVer.size() != nN) e->leafVer.assign(nN, 0);
   LeafConst* lc = e->hLeafStage;
   if (e->model == DCSMC_MODEL_MULTILEVEL)
-    for (int n = 0; n < nN; ++n) leafConstFor(e, n, lc[n]);
+    for (int n = lo; n < hi; ++n) leafConstFor(e, n, lc[n]);
   else
-    memset(lc, 0, sizeof(LeafConst) * nN);
-  CK(cudaMemcpyAsync(e->dLeaf, lc, sizeof(LeafConst) * nN, cudaMemcpyHostToDevice, e->stream));
-  e->pendingH2D += (int64_t)(sizeof(LeafConst) * nN);
-  e->leafDirty = false;
+    memset(lc + lo, 0, sizeof(LeafConst) * (size_t)(hi - lo));
+  for (int n = lo; n < hi; ++n) e->leafVer[n] = e->leafVersion;
+  CK(cudaMemcpyAsync(e->dLeaf + lo, lc + lo, sizeof(LeafConst) * (size_t)(hi - lo), cudaMemcpyHostToDevice, e->stream));
+  e->pendingH2D += (int64_t)(sizeof(LeafConst) * (size_t)(hi - lo));
   return DCSMC_OK;
+}
+int uploadLeafTable(dcsmc_engine* e) {
+  int rc = uploadLeafRange(e, 0, e->nNodes);
+  if (rc == DCSMC_OK) e->leafFullVersion = e->leafVersion;
+  return rc;
+}
+
+// before a plan runs: the leaf entries it reads — every node of its roots' subtrees (a contiguous id range when
+// the nodes are numbered in pre-order, as tree.py and ddc_main.cpp do) and the children of its nodes
+int uploadLeafForPlan(dcsmc_engine* e, const std::vector<int>& roots, const Plan& plan) {
+  if (e->leafFullVersion == e->leafVersion) return DCSMC_OK;
+  if ((int)e->leafVer.size() != e->nNodes) e->leafVer.assign(e->nNodes, 0);
+  int rc;
+  if (e->preorder) {
+    for (int r : roots) {
+      const int lo = r, hi = r + e->subtreeSize[r];
+      bool stale = false;
+      for (int n = lo; n < hi && !stale; ++n) stale = e->leafVer[n] != e->leafVersion;
+      if (stale && (rc = uploadLeafRange(e, lo, hi))) return rc;
+    }
+    for (int n : plan.stepNodes)
+      for (int c = e->childOffsets[n]; c < e->childOffsets[n + 1]; ++c) {
+        const int ch = e->children[c];
+        if (e->leafVer[ch] != e->leafVersion && (rc = uploadLeafRange(e, ch, ch + 1))) return rc;
+      }
+    return DCSMC_OK;
+  }
+  return uploadLeafTable(e);
 }
 
 int uploadTables(dcsmc_engine* e) {
-  if (!e->tablesDirty) return e->leafDirty ? uploadLeafTable(e) : DCSMC_OK;
+  if (!e->tablesDirty) return DCSMC_OK;
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
   if (e->model < 0) return e->fail(DCSMC_ESTATE, "no proposal model set (dcsmc_set_*_model)");
   const int nN = e->nNodes;
@@ -513,6 +548,8 @@ int uploadTables(dcsmc_engine* e) {
                      cudaMemcpyHostToDevice, e->stream));
   e->pendingH2D += (int64_t)(sizeof(int32_t) * e->children.size() + sizeof(uint64_t) * nN);
   int rcLeaf;
+  e->leafVersion++;
+  e->leafVer.clear();
   if ((rcLeaf = uploadLeafTable(e))) return rcLeaf;
   std::vector<uint64_t> js(nN, 0);
   for (int n = 0; n < nN; ++n)
@@ -1427,6 +1464,7 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
         e->resident = cp.resident;
         e->imported = cp.imported;
       }
+      if ((rc = uploadLeafForPlan(e, roots, cp.plan))) return rc;
       return executePlan(e, cp.plan, &cp);
     }
     // contextual plan: valid when the allocator and the children are in the state it was made for (the schedule
@@ -1441,6 +1479,7 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
     }
     e->freeBySize = cp.freeBySize;
     e->poolTop = cp.poolTop;
+    if ((rc = uploadLeafForPlan(e, roots, cp.plan))) return rc;
     return executePlan(e, cp.plan, &cp);
   }
   Plan plan;
@@ -1466,6 +1505,7 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
     e->undoOn = false;
   }
   if (rc) return rc;
+  if ((rc = uploadLeafForPlan(e, roots, plan))) return rc;
   if (!record) return executePlan(e, plan);
   cp->plan = plan;
   cp->freeBySize = e->freeBySize;
@@ -1733,6 +1773,18 @@ int32_t dcsmc_set_tree(dcsmc_engine* e, int32_t nNodes, int32_t root, const int3
   e->children.assign(children, children + nEdges);
   e->parent = parent;
   e->height = height;
+  // subtree sizes; pre-order numbering (root 0, a subtree = the id range [r, r + size)) lets a rank upload and plan
+  // only its own part of a large tree
+  e->subtreeSize.assign(nNodes, 1);
+  for (int k = nNodes - 1; k > 0; --k) e->subtreeSize[parent[order[k]]] += e->subtreeSize[order[k]];
+  e->preorder = root == 0;
+  for (int n = 0; n < nNodes && e->preorder; ++n) {
+    int next = n + 1;
+    for (int c = childOffsets[n]; c < childOffsets[n + 1]; ++c) {
+      if (children[c] != next) { e->preorder = false; break; }
+      next += e->subtreeSize[children[c]];
+    }
+  }
   e->depth.assign(nNodes, 0);  // Node.level() (prototype/Node.java:72-75): root = 0
   for (int k = 1; k < nNodes; ++k) e->depth[order[k]] = e->depth[parent[order[k]]] + 1;
   e->javaHash.clear();
@@ -1787,7 +1839,7 @@ int32_t dcsmc_set_multilevel_model(dcsmc_engine* e, const int32_t* leafKind, con
   // the memory plan depends on the leaf KINDS only (observed leaves hold no population); new counts /
   // observations on the same kinds are new input data for the same plan
   if (sameFamily && oldKind == e->leafKind)
-    e->leafDirty = true;
+    e->leafVersion++;
   else
     e->tablesDirty = true;
   return DCSMC_OK;
@@ -2296,7 +2348,7 @@ int32_t dcsmc_population_import_peer(dcsmc_engine* e, const int32_t* nodes, cons
     z.logScaling = d.logScaling;
     z.logZ = d.logZ;
     z.resampled = d.resampled;
-    z.done = 1;
+    z.done = 2;  // a population computed elsewhere (k_stats_matrix counts done == 1 only)
     hSt[k] = z;
     dcsmc_node_stats_t& o = e->hStats[node];
     o.ess = d.ess;
@@ -2483,9 +2535,21 @@ int32_t dcsmc_population_import_peer_device(dcsmc_engine* e, const int32_t* node
   return DCSMC_OK;
 }
 
+int32_t dcsmc_stats_matrix_device(dcsmc_engine* e, void* deviceDst) {
+  if (!e || !deviceDst) return DCSMC_EINVAL;
+  if (e->nNodes <= 0 || e->dStats == nullptr || e->tablesDirty) return e->fail(DCSMC_ESTATE, "nothing has run on this engine yet");
+  CK(cudaSetDevice(e->opt.device));
+  e->info.kernelLaunches++;
+  k_stats_matrix<<<(e->nNodes + 255) / 256, 256, 0, e->stream>>>(e->dStats, e->nNodes, static_cast<double*>(deviceDst));
+  CK(cudaGetLastError());
+  return DCSMC_OK;
+}
+
 int32_t dcsmc_reset_populations(dcsmc_engine* e) {
   if (!e) return DCSMC_EINVAL;
   e->pendNodes.clear();  // statistics nobody asked for
+  if (e->dStats != nullptr && !e->tablesDirty && e->nNodes > 0 && cudaSetDevice(e->opt.device) == cudaSuccess)
+    cudaMemsetAsync(e->dStats, 0, sizeof(NodeStats) * (size_t)e->nNodes, e->stream);  // nothing is computed any more
   // O(nodes touched since the last reset), not O(nNodes): a rank of a sharded run only ever touches
   // its own part of a large tree
   for (int n : e->externalNodes)

@@ -415,6 +415,7 @@ class DistributedDC:
         t0 = time.perf_counter()
         self._stats = None  # gathered lazily (a collective when sharded): see `stats`
         self._summaries = None
+        self._nodeMs = None  # per-node times exist for the profiled run of start() only
         if dist is None:
             self.engine.run()
             info = self.engine.run_info()
@@ -711,17 +712,37 @@ class DistributedDC:
         every rank must call (start() does)."""
         if self._stats is not None:
             return self._stats
-        st = self.engine.all_node_stats()
         dist = self._dist()
         if dist is None:
-            self._stats = st
-            return st
+            self._stats = self.engine.all_node_stats()
+            return self._stats
         import torch
 
+        nodeMs = getattr(self, "_nodeMs", None)
+        if hasattr(self.engine, "stats_matrix_device") and torch.cuda.is_available() and nodeMs is None:
+            # the table is assembled on the device: every rank contributes the nodes it computed, one all-reduce
+            # ordered on the engine's stream, one copy to the host — no per-node work in Python
+            dev = torch.device("cuda", self.engine.options.device)
+            nN = self.csr.nNodes
+            buf = getattr(self, "_statsBuf", None)
+            if buf is None or buf.numel() != 6 * nN:
+                buf = self._statsBuf = torch.empty(6 * nN, dtype=torch.float64, device=dev)
+                self._statsStream = torch.cuda.ExternalStream(self.engine.stream(), device=dev)
+            self.engine.stats_matrix_device(buf.data_ptr())
+            with torch.cuda.stream(self._statsStream):
+                dist.all_reduce(buf)
+                mat = buf.cpu().numpy().reshape(6, nN)
+            if not np.all(mat[5] == 1.0):
+                raise RuntimeError(f"sharded run: {int((mat[5] != 1.0).sum())} nodes were computed by no rank or by several")
+            out = {k: mat[i] for i, k in enumerate(["ess", "relEss", "logNormEstimate", "logScaling"])}
+            out["resampled"] = mat[4].astype(np.int32)
+            out["done"] = np.ones(nN, np.int32)
+            self._stats = out
+            return out
+        st = self.engine.all_node_stats()
         rank = dist.get_rank()
         own = self._nodeOwner
         keys = ["ess", "relEss", "logNormEstimate", "logScaling"]
-        nodeMs = getattr(self, "_nodeMs", None)
         mat = np.stack([np.where(own == rank, st[k], 0.0) for k in keys] + [np.where(own == rank, st["resampled"], 0).astype(np.float64)]
                        + [np.where(own == rank, nodeMs if nodeMs is not None else 0.0, 0.0)])
         dev = torch.device("cuda", self.engine.options.device) if torch.cuda.is_available() else torch.device("cpu")

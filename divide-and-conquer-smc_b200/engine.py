@@ -266,6 +266,11 @@ class Engine:
             self._h, _ptr(r, C.c_int32), _ptr(q, C.c_int32), len(r), buf, C.c_void_p(device_stats_ptr), _ptr(ix, C.c_int32),
             int(n_records)))
 
+    def stats_matrix_device(self, device_ptr: int):
+        """dcsmc_stats_matrix_device: [6][nNodes] doubles (ess, relEss, logNormEstimate, logScaling, resampled,
+        computedHere) of the nodes this engine computed, on the device."""
+        self._ck(self._L.dcsmc_stats_matrix_device(self._h, C.c_void_p(device_ptr)))
+
     def reset_populations(self):
         self._ck(self._L.dcsmc_reset_populations(self._h))
 

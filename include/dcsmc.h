@@ -313,6 +313,12 @@ int32_t dcsmc_population_import_peer_device(dcsmc_engine* e, const int32_t* node
                                             const void* descs, const void* deviceStats, const int32_t* statIndex,
                                             int32_t nRecords);
 
+/* The per-node statistics of the nodes THIS engine computed since the last reset, zeros elsewhere, as a DEVICE
+ * matrix of doubles [6][nNodes]: ess, relEss, logNormEstimate, logScaling, resampled, computedHere. Summed over the
+ * ranks of a sharded run (an all-reduce ordered on dcsmc_stream) it is the whole tree's `timing` table
+ * (DefaultProcessorFactory.java:45-52) without any per-node work on the host. */
+int32_t dcsmc_stats_matrix_device(dcsmc_engine* e, void* deviceDst);
+
 /* ---- planning without a device ---------------------------------------------------------
  * The schedule and the memory plan are a pure function of (options, tree, leaf kinds, pool size): this
  * entry point runs the planner on the host only — no CUDA device is needed or touched — and reports what
