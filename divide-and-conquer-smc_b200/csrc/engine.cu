@@ -74,6 +74,8 @@ struct CachedPlan {
   std::vector<char> inPlan;  // per node: computed by this plan
   std::vector<int> finalResident;  // nodes still resident when the plan has run (its roots, unless retained)
   int32_t* dStepNodes = nullptr;   // device copy of plan.stepNodes
+  std::vector<std::pair<int, int>> leafRanges;  // id ranges of the leaf entries the plan reads
+  uint64_t leafVersion = 0;        // leaf data version those entries were last uploaded at
   bool onDevice = false;           // step list + descriptors of the plan's nodes are on the device, untouched since
   // the plan's whole launch sequence as a CUDA graph (captured on its first replay)
   mutable cudaGraphExec_t graphExec = nullptr;
@@ -483,6 +485,7 @@ int uploadLeafRange(dcsmc_engine* e, int lo, int hi) {
   else
     memset(lc + lo, 0, sizeof(LeafConst) * (size_t)(hi - lo));
   for (int n = lo; n < hi; ++n) e->leafVer[n] = e->leafVersion;
+  if (getenv("DCSMC_HOSTPROF")) fprintf(stderr, "[dcsmc hostprof] leaf entries [%d, %d) uploaded (version %llu)\n", lo, hi, (unsigned long long)e->leafVersion);
   CK(cudaMemcpyAsync(e->dLeaf + lo, lc + lo, sizeof(LeafConst) * (size_t)(hi - lo), cudaMemcpyHostToDevice, e->stream));
   e->pendingH2D += (int64_t)(sizeof(LeafConst) * (size_t)(hi - lo));
   return DCSMC_OK;
@@ -493,31 +496,47 @@ int uploadLeafTable(dcsmc_engine* e) {
   return rc;
 }
 
-// before a plan runs: the leaf entries it reads — every node of its roots' subtrees (a contiguous id range when
-// the nodes are numbered in pre-order, as tree.py and ddc_main.cpp do) and the children of its nodes
-int uploadLeafForPlan(dcsmc_engine* e, const std::vector<int>& roots, const Plan& plan) {
-  if (e->leafFullVersion == e->leafVersion) return DCSMC_OK;
-  if ((int)e->leafVer.size() != e->nNodes) e->leafVer.assign(e->nNodes, 0);
-  int rc;
-  if (e->preorder) {
-    for (int r : roots) {
-      const int lo = r, hi = r + e->subtreeSize[r];
-      bool stale = false;
-      for (int n = lo; n < hi && !stale; ++n) stale = e->leafVer[n] != e->leafVersion;
-      if (stale && (rc = uploadLeafRange(e, lo, hi))) return rc;
-    }
-    for (int n : plan.stepNodes)
-      for (int c = e->childOffsets[n]; c < e->childOffsets[n + 1]; ++c) {
-        const int ch = e->children[c];
-        if (e->leafVer[ch] != e->leafVersion && (rc = uploadLeafRange(e, ch, ch + 1))) return rc;
-      }
-    return DCSMC_OK;
+// The leaf entries a plan reads: its own nodes and their children (an imported or still resident child's entry
+// is read for its observation), as contiguous id ranges — a rank's subtrees are a handful of ranges when the nodes
+// are numbered in pre-order, as tree.py and ddc_main.cpp do.
+std::vector<std::pair<int, int>> leafRangesOf(const dcsmc_engine* e, const Plan& plan) {
+  std::vector<int> ids(plan.stepNodes.begin(), plan.stepNodes.end());
+  for (int n : plan.stepNodes)
+    for (int c = e->childOffsets[n]; c < e->childOffsets[n + 1]; ++c) ids.push_back(e->children[c]);
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  std::vector<std::pair<int, int>> out;
+  for (int id : ids) {
+    if (!out.empty() && out.back().second == id)
+      out.back().second = id + 1;
+    else
+      out.push_back({id, id + 1});
   }
-  return uploadLeafTable(e);
+  return out;
+}
+
+// before a plan runs: upload the entries of its ranges that are older than the current leaf data
+int uploadLeafForPlan(dcsmc_engine* e, const Plan& plan, CachedPlan* cached) {
+  if (e->leafFullVersion == e->leafVersion) return DCSMC_OK;
+  if (cached && cached->leafVersion == e->leafVersion) return DCSMC_OK;
+  if ((int)e->leafVer.size() != e->nNodes) e->leafVer.assign(e->nNodes, 0);
+  std::vector<std::pair<int, int>> tmp;
+  if (cached && cached->leafRanges.empty()) cached->leafRanges = leafRangesOf(e, plan);
+  if (!cached) tmp = leafRangesOf(e, plan);
+  const std::vector<std::pair<int, int>>& ranges = cached ? cached->leafRanges : tmp;
+  int rc;
+  for (const auto& r : ranges) {
+    bool stale = false;  // another plan of this run may already have brought the range up to date (shared children)
+    for (int n = r.first; n < r.second && !stale; ++n) stale = e->leafVer[n] != e->leafVersion;
+    if (stale && (rc = uploadLeafRange(e, r.first, r.second))) return rc;
+  }
+  if (cached) cached->leafVersion = e->leafVersion;
+  return DCSMC_OK;
 }
 
 int uploadTables(dcsmc_engine* e) {
   if (!e->tablesDirty) return DCSMC_OK;
+  if (getenv("DCSMC_HOSTPROF")) fprintf(stderr, "[dcsmc hostprof] full table upload (%d nodes), plans dropped\n", e->nNodes);
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
   if (e->model < 0) return e->fail(DCSMC_ESTATE, "no proposal model set (dcsmc_set_*_model)");
   const int nN = e->nNodes;
@@ -1464,7 +1483,7 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
         e->resident = cp.resident;
         e->imported = cp.imported;
       }
-      if ((rc = uploadLeafForPlan(e, roots, cp.plan))) return rc;
+      if ((rc = uploadLeafForPlan(e, cp.plan, &cp))) return rc;
       return executePlan(e, cp.plan, &cp);
     }
     // contextual plan: valid when the allocator and the children are in the state it was made for (the schedule
@@ -1479,7 +1498,7 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
     }
     e->freeBySize = cp.freeBySize;
     e->poolTop = cp.poolTop;
-    if ((rc = uploadLeafForPlan(e, roots, cp.plan))) return rc;
+    if ((rc = uploadLeafForPlan(e, cp.plan, &cp))) return rc;
     return executePlan(e, cp.plan, &cp);
   }
   Plan plan;
@@ -1505,8 +1524,10 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
     e->undoOn = false;
   }
   if (rc) return rc;
-  if ((rc = uploadLeafForPlan(e, roots, plan))) return rc;
-  if (!record) return executePlan(e, plan);
+  if (!record) {
+    if ((rc = uploadLeafForPlan(e, plan, nullptr))) return rc;
+    return executePlan(e, plan);
+  }
   cp->plan = plan;
   cp->freeBySize = e->freeBySize;
   cp->poolTop = e->poolTop;
@@ -1526,6 +1547,7 @@ int runRoots(dcsmc_engine* e, const std::vector<int>& roots) {
   }
   e->planCache.push_back(std::move(cp));
   CachedPlan* held = e->planCache.back().get();
+  if ((rc = uploadLeafForPlan(e, held->plan, held))) return rc;
   return executePlan(e, held->plan, held);
 }
 

@@ -727,11 +727,14 @@ class DistributedDC:
             buf = getattr(self, "_statsBuf", None)
             if buf is None or buf.numel() != 6 * nN:
                 buf = self._statsBuf = torch.empty(6 * nN, dtype=torch.float64, device=dev)
+                self._statsHost = torch.empty(6 * nN, dtype=torch.float64, pin_memory=True)
                 self._statsStream = torch.cuda.ExternalStream(self.engine.stream(), device=dev)
             self.engine.stats_matrix_device(buf.data_ptr())
             with torch.cuda.stream(self._statsStream):
                 dist.all_reduce(buf)
-                mat = buf.cpu().numpy().reshape(6, nN)
+                self._statsHost.copy_(buf, non_blocking=True)
+                self._statsStream.synchronize()
+            mat = self._statsHost.numpy().reshape(6, nN).copy()
             if not np.all(mat[5] == 1.0):
                 raise RuntimeError(f"sharded run: {int((mat[5] != 1.0).sum())} nodes were computed by no rank or by several")
             out = {k: mat[i] for i, k in enumerate(["ess", "relEss", "logNormEstimate", "logScaling"])}
@@ -890,6 +893,20 @@ class DistributedDC:
         return self._rootPopulation
 
     def close(self):
+        # tensors that were used on the engine's stream must go before the stream does (the caching allocator
+        # records an event on every stream a block was used on when the block is freed)
+        for name in ("_statsBuf", "_statsHost", "_statsStream", "_p2pBufs", "_p2pStream", "_p2pSync", "_xferBufs"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        self._p2pStatic = None
+        self._p2pLevels = None
         if self.engine is not None:
+            try:
+                import torch
+
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
+            except Exception:
+                pass
             self.engine.close()
             self.engine = None
