@@ -191,6 +191,10 @@ struct dcsmc_engine {
   size_t leafSmemSet[3] = {0, 0, 0};
   size_t smallSmemSet[3] = {0, 0, 0};
   size_t smallSmemSet512[3] = {0, 0, 0};
+  size_t fusedSmemSet[3] = {0, 0, 0};
+  size_t fusedSmemSet512[3] = {0, 0, 0};
+  bool fuseSmall = true;       // k_node_fused for small populations (DCSMC_FUSE_SMALL=0: propose + k_node_small)
+  int fuseMinNodes = 148;      // ... for level batches of at least this many nodes (DCSMC_FUSE_MIN_NODES)
   std::vector<std::unique_ptr<CachedPlan>> planCache;
   // deferred mode (dcsmc_begin_deferred .. dcsmc_sync): run calls only enqueue; one host synchronisation at the end
   bool deferred = false;
@@ -934,6 +938,12 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
   // leaf kernel does the dart work itself (k_finalize still records the statistics)
   const bool javaSums = e->opt.sumMode == DCSMC_SUM_JAVA;
   const bool leafFused = !javaSums && st.leaf && e->model == DCSMC_MODEL_MULTILEVEL && 1.0 < e->opt.relativeEssThreshold;
+  // one block per node: pays when the level has enough nodes to fill the GPU (the few top levels of a tree keep
+  // the two-kernel form, whose propose kernel spreads a node over many blocks)
+  bool fusedSmall = !st.leaf && !javaSums && N <= SMALLN_MAX && e->model == DCSMC_MODEL_MULTILEVEL && e->fuseSmall && sR == sP &&
+                    st.count >= e->fuseMinNodes;
+  if (fusedSmall)
+    for (int k = 0; k < st.count && fusedSmall; ++k) fusedSmall = nChildrenOf(e, e->planStepNodes[st.offset + k]) <= FUSED_CMAX;
 
   if (e->model == DCSMC_MODEL_MARKOV) {
     ProfScope p(e, DCSMC_K_MARKOV, sP);
@@ -956,6 +966,28 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     ProfScope p(e, DCSMC_K_LEAF, sP);
     k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS,
                           leafSmem, sP>>>(c, blocksPerNode, CH, mode);
+  } else if (fusedSmall) {
+    // the population fits in shared memory and the children's descriptors too: one block per node does the whole
+    // node step (k_node_fused), the log weights never leave the SM
+    const size_t smem = smalln_smem_bytes(c.Npad);
+    const bool wideBlk = smalln_threads(c.Npad) == 1024;
+    size_t& smemSet = wideBlk ? e->fusedSmemSet[RNG] : e->fusedSmemSet512[RNG];
+    if (smem > smemSet) {
+      if (wideBlk)
+        CK(cudaFuncSetAttribute(k_node_fused<RNG, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else
+        CK(cudaFuncSetAttribute(k_node_fused<RNG, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smemSet = smem;
+    }
+    {
+      ProfScope p(e, DCSMC_K_INTERNAL, sP);
+      if (wideBlk)
+        k_node_fused<RNG, 1024><<<st.count, 1024, smem, sP>>>(c);
+      else
+        k_node_fused<RNG, 512><<<st.count, 512, smem, sP>>>(c);
+    }
+    CK(cudaGetLastError());
+    return launchSummaries<RNG>(e, c, st, sP);
   } else {
     {
       ProfScope p(e, DCSMC_K_INTERNAL, sP);
@@ -1087,6 +1119,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.invB = e->invB;
   c.javaSums = e->opt.sumMode == DCSMC_SUM_JAVA;
   c.skipObs = skipObservedLeaves(e);
+  c.keepLogw = (e->opt.retainPopulations || !(1.0 < e->opt.relativeEssThreshold)) ? 1 : 0;
   c.uniformLogW = uniformLeafLogW(e);
   c.summ = e->dSumm;
   c.sumScratch = e->dSumScratch;
@@ -1666,6 +1699,9 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   cudaDeviceGetAttribute(&e->smCount, cudaDevAttrMultiProcessorCount, opt->device);
   if (e->smCount <= 0) e->smCount = 148;
   if (const char* v = getenv("DCSMC_GRAPHS")) e->useGraphs = atoi(v) != 0;
+  if (const char* v = getenv("DCSMC_FUSE_SMALL")) e->fuseSmall = atoi(v) != 0;
+  e->fuseMinNodes = e->smCount;
+  if (const char* v = getenv("DCSMC_FUSE_MIN_NODES")) e->fuseMinNodes = std::max(1, atoi(v));
   if (const char* v = getenv("DCSMC_OVERLAP_CHUNKS")) e->overlapChunks = std::max(1, atoi(v));
   if (cudaSetDevice(opt->device) != cudaSuccess ||
       cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prLow) != cudaSuccess ||
