@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libdcsmc.so")
+# DCSMC_LIB selects another build of the same sources (profiles/: timing-only experiment variants)
+LIB_PATH = os.environ.get("DCSMC_LIB") or os.path.join(HERE, "csrc", "libdcsmc.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, 1, 2, 3, 4
 MULTINOMIAL, STRATIFIED = 0, 1

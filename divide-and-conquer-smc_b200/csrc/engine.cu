@@ -207,6 +207,15 @@ struct dcsmc_engine {
   size_t stageCap = 0;
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
   size_t offspringCap = 0;
+  // partitioned multinomial resampling of large populations (k_dart_partition / k_seg_resample)
+  bool partitionDarts = true;     // DCSMC_PARTITION_DARTS=0: k_darts_count + k_expand
+  double* dDartBuf = nullptr;
+  size_t dartBufCap = 0;
+  int32_t* dChunkBin = nullptr;
+  size_t chunkBinCap = 0;
+  int32_t* dSegTotal = nullptr;
+  size_t segTotalCap = 0;
+  bool segSmemSet = false;
 
   // measurement
   dcsmc_run_info info{};
@@ -1052,6 +1061,33 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     ProfScope p(e, DCSMC_K_FINALIZE, sR);
     k_finalize<<<(st.count + 127) / 128, 128, 0, sR>>>(c);
   }
+  if (!st.leaf && !javaSums && e->opt.resamplingScheme == DCSMC_MULTINOMIAL && e->partitionDarts && e->dDartBuf != nullptr) {
+    // darts grouped by CDF segment, then one block per segment works in shared memory (k_dart_partition /
+    // k_seg_resample): no inverse index, no global offspring counters, no expansion kernel
+    const int K = dp_segs(N), nCh = dp_chunks(N);
+    c.dpSegs = K;
+    c.dpChunks = nCh;
+    c.dpStride = dp_stride(N);
+    c.dartBuf = e->dDartBuf + (size_t)ch.lo * c.dpStride;
+    c.chunkBin = e->dChunkBin + (size_t)ch.lo * nCh * (size_t)(K + 1);
+    c.segTotal = e->dSegTotal + (size_t)ch.lo * K;
+    CK(cudaMemsetAsync(c.segTotal, 0, (size_t)st.count * K * sizeof(int32_t), sR));
+    const size_t smemA = sizeof(double) * ((size_t)K + DP_CHUNK) + sizeof(int) * ((size_t)K + 1);
+    {
+      ProfScope p(e, DCSMC_K_DARTS, sR);
+      k_dart_partition<RNG><<<(unsigned)((size_t)st.count * nCh), DP_THREADS, smemA, sR>>>(c);
+    }
+    if (!e->segSmemSet) {
+      CK(cudaFuncSetAttribute(k_seg_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_resample_smem_bytes()));
+      e->segSmemSet = true;
+    }
+    {
+      ProfScope p(e, DCSMC_K_RESAMPLE, sR);
+      k_seg_resample<<<(unsigned)((size_t)st.count * K), SR_THREADS, seg_resample_smem_bytes(), sR>>>(c);
+    }
+    CK(cudaGetLastError());
+    return launchSummaries<RNG>(e, c, st, sR);
+  }
   if (!st.leaf || javaSums) {
     const int tilesT = (c.invB + 1 + RESAMPLE_THREADS - 1) / RESAMPLE_THREADS;
     ProfScope p(e, DCSMC_K_RESAMPLE, sR);
@@ -1223,6 +1259,12 @@ int executePlan(dcsmc_engine* e, Plan& plan, CachedPlan* cached = nullptr) {
   CK(grow((void**)&e->dInvTable, e->invTableCap, std::max<size_t>(1, maxInternalStep * ((size_t)e->invB + 1)), sizeof(int32_t)));
   if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL)
     CK(grow((void**)&e->dOffspring, e->offspringCap, maxStep * (size_t)e->Npad, sizeof(int32_t)));
+  if (e->opt.resamplingScheme == DCSMC_MULTINOMIAL && e->partitionDarts && N > SMALLN_MAX && e->opt.sumMode == DCSMC_SUM_EXACT &&
+      maxInternalStep > 0) {
+    CK(grow((void**)&e->dDartBuf, e->dartBufCap, maxInternalStep * (size_t)dp_stride(N), sizeof(double)));
+    CK(grow((void**)&e->dChunkBin, e->chunkBinCap, maxInternalStep * (size_t)dp_chunks(N) * (size_t)(dp_segs(N) + 1), sizeof(int32_t)));
+    CK(grow((void**)&e->dSegTotal, e->segTotalCap, maxInternalStep * (size_t)dp_segs(N), sizeof(int32_t)));
+  }
   if (e->opt.retainSamples && e->opt.levelCutOffForOutput > 0 && e->model == DCSMC_MODEL_MULTILEVEL) {
     // every summary node of the plan owns a fixed range of the sample store, in launch order
     if ((int)e->sampleBase.size() != e->nNodes) e->sampleBase.assign(e->nNodes, -1);
@@ -1700,6 +1742,7 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   if (e->smCount <= 0) e->smCount = 148;
   if (const char* v = getenv("DCSMC_GRAPHS")) e->useGraphs = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_FUSE_SMALL")) e->fuseSmall = atoi(v) != 0;
+  if (const char* v = getenv("DCSMC_PARTITION_DARTS")) e->partitionDarts = atoi(v) != 0;
   e->fuseMinNodes = e->smCount;
   if (const char* v = getenv("DCSMC_FUSE_MIN_NODES")) e->fuseMinNodes = std::max(1, atoi(v));
   if (const char* v = getenv("DCSMC_OVERLAP_CHUNKS")) e->overlapChunks = std::max(1, atoi(v));
@@ -1756,7 +1799,8 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   if (e->dSumm) cudaFree(e->dSumm);
   if (e->dSumScratch) cudaFree(e->dSumScratch);
   void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodesTmp, e->dInj, e->dJavaState,
-                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable};
+                  e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable,
+                  e->dDartBuf, e->dChunkBin, e->dSegTotal};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   chk("tables");
@@ -2717,6 +2761,9 @@ int32_t dcsmc_plan_query(const dcsmc_options* opt, int32_t nNodes, const int32_t
   size_t scratch = (maxStep * descWordsPerNode(N) + 2 * MAX_CHUNKS + 2) * sizeof(unsigned long long);
   if (!small) scratch += maxInternalStep * (size_t)e->Npad * sizeof(double) + maxInternalStep * (invB + 1) * sizeof(int32_t);
   if (opt->resamplingScheme == DCSMC_MULTINOMIAL) scratch += maxStep * (size_t)e->Npad * sizeof(int32_t);
+  if (opt->resamplingScheme == DCSMC_MULTINOMIAL && !small && opt->sumMode == DCSMC_SUM_EXACT)  // partitioned darts
+    scratch += maxInternalStep * ((size_t)dp_stride(N) * sizeof(double) +
+                                  ((size_t)dp_chunks(N) * (size_t)(dp_segs(N) + 1) + (size_t)dp_segs(N)) * sizeof(int32_t));
   out->peakBytes = (int64_t)e->poolPeak;
   out->scratchBytes = (int64_t)scratch;
   out->tableBytes = (int64_t)((sizeof(NodeDev) + sizeof(NodeStats) + sizeof(LeafConst) + sizeof(uint64_t) + sizeof(double*) +
