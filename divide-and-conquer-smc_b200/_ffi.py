@@ -103,7 +103,7 @@ SYMBOLS = [
     "dcsmc_abi_version", "dcsmc_options_default", "dcsmc_create", "dcsmc_destroy", "dcsmc_last_error",
     "dcsmc_set_tree", "dcsmc_set_node_seeds", "dcsmc_set_multilevel_model", "dcsmc_set_markov_model",
     "dcsmc_slots_per_particle", "dcsmc_inject_uniforms", "dcsmc_run", "dcsmc_run_subtrees",
-    "dcsmc_run_nodes", "dcsmc_node_stats", "dcsmc_all_node_stats", "dcsmc_population_copy_to_host",
+    "dcsmc_run_nodes", "dcsmc_node_stats", "dcsmc_all_node_stats", "dcsmc_all_node_stats_columns", "dcsmc_population_copy_to_host",
     "dcsmc_debug_copy_node", "dcsmc_population_packed_bytes", "dcsmc_population_pack",
     "dcsmc_population_unpack", "dcsmc_population_release", "dcsmc_last_run_info",
     "dcsmc_profile_enable", "dcsmc_profile_get", "dcsmc_debug_eval", "dcsmc_reset_populations",
@@ -147,6 +147,7 @@ def lib():
     L.dcsmc_run_nodes.argtypes = [vp, P(i32), i32]
     L.dcsmc_node_stats.argtypes = [vp, i32, P(NodeStats)]
     L.dcsmc_all_node_stats.argtypes = [vp, P(NodeStats)]
+    L.dcsmc_all_node_stats_columns.argtypes = [vp] + [P(dbl)] * 4 + [P(i32)] * 2
     L.dcsmc_population_copy_to_host.argtypes = [vp, i32, P(dbl), P(i32), P(dbl)]
     L.dcsmc_debug_copy_node.argtypes = [vp, i32, P(dbl), P(i32), P(dbl), P(i32)]
     L.dcsmc_population_packed_bytes.argtypes = [vp]

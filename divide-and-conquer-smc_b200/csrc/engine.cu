@@ -47,6 +47,10 @@ struct Slot {
 struct Plan {
   std::vector<Step> steps;
   std::vector<int32_t> stepNodes;
+  // the same nodes in ascending id order: the order in which their statistics leave the device, so that the host
+  // scatters them into its per-node tables front to back (in plan order — leaves first, level by level — the scatter
+  // of a 131 071-node tree was 3 ms of cache misses per run)
+  std::vector<int32_t> exportOrder;
 };
 
 // A plan is a pure function of (tree, model, options, roots, pool state at entry): cached together with the pool
@@ -118,6 +122,7 @@ struct dcsmc_engine {
   int32_t* dErr = nullptr;           // device-side consistency flag of deferred imports (read at dcsmc_sync)
   int32_t* hErr = nullptr;           // pinned
   LeafConst* dLeaf = nullptr;
+  double* dLeafObs = nullptr;             // observation of every Gaussian leaf, by node id (8 B per node instead of a LeafConst)
   int32_t* dChildren = nullptr;
   int32_t* dStepNodesTmp = nullptr;  // step lists of the current uncached plan
   size_t stepNodesTmpCap = 0;
@@ -163,6 +168,8 @@ struct dcsmc_engine {
   int64_t poolGeneration = 0;
   char *dImp = nullptr, *hImp = nullptr;  // dcsmc_population_import_peer staging
   LeafConst* hLeafStage = nullptr;        // pinned staging of the leaf table
+  double* hObsStage = nullptr;            // ... and of the observations
+  std::vector<int32_t> binomPrefix;       // binomial leaves among the nodes [0, n): which id ranges need LeafConst entries
   size_t leafStageCap = 0;
   size_t impCap = 0;
   cudaEvent_t evImp = nullptr;            // the last upload out of hImp
@@ -189,6 +196,7 @@ struct dcsmc_engine {
   size_t invTableCap = 0;
   int invB = 1;
   size_t leafSmemSet[3] = {0, 0, 0};
+  size_t leaf2SmemSet[3] = {0, 0, 0};
   size_t smallSmemSet[3] = {0, 0, 0};
   size_t smallSmemSet512[3] = {0, 0, 0};
   size_t fusedSmemSet[3] = {0, 0, 0};
@@ -209,6 +217,9 @@ struct dcsmc_engine {
   size_t offspringCap = 0;
   // partitioned multinomial resampling of large populations (k_dart_partition / k_seg_resample)
   bool partitionDarts = true;     // DCSMC_PARTITION_DARTS=0: k_darts_count + k_expand
+  int leafVariant = 2;            // DCSMC_LEAF_V=1: k_leaf_propose (r01) instead of k_leaf_propose2
+  bool leafKidsKernel = true;     // DCSMC_LEAFKIDS=0: the generic merge kernel also for the level above the leaves
+  int scanVariant = 2;            // DCSMC_SCAN_V=1: k_scan (r01) instead of k_scan2
   double* dDartBuf = nullptr;
   size_t dartBufCap = 0;
   int32_t* dChunkBin = nullptr;
@@ -395,11 +406,7 @@ void fillNodeDev(dcsmc_engine* e, int n) {
 
 void leafConstFor(const dcsmc_engine* e, int node, LeafConst& lc) {
   memset(&lc, 0, sizeof lc);
-  if (nodeKind(e, node) == KIND_LEAF_GAUSS) {
-    lc.obs = e->leafObs.empty() ? 0.0 : e->leafObs[node];
-    return;
-  }
-  if (nodeKind(e, node) != KIND_LEAF_BINOMIAL) return;
+  if (nodeKind(e, node) != KIND_LEAF_BINOMIAL) return;  // observed leaves: their datum lives in dLeafObs
   // MultiLevelProposalFactory.build (MultiLevelProposalFactory.java:40-49): Beta(1+s, 1+(n-s)),
   // then the constants of Cheng's BB/BC samplers (commons-math3 BetaDistribution.sample()).
   const int32_t n = e->nTrials[node], s = e->nSuccesses[node];
@@ -486,21 +493,39 @@ int uploadLeafRange(dcsmc_engine* e, int lo, int hi) {
   const int nN = e->nNodes;
   if ((size_t)nN > e->leafStageCap) {
     if (e->hLeafStage) cudaFreeHost(e->hLeafStage);
+  if (e->hObsStage) cudaFreeHost(e->hObsStage);
     e->hLeafStage = nullptr;
     e->leafStageCap = 0;
+    if (e->hObsStage) cudaFreeHost(e->hObsStage);
+    e->hObsStage = nullptr;
     CK(cudaMallocHost((void**)&e->hLeafStage, sizeof(LeafConst) * (size_t)nN));
+    CK(cudaMallocHost((void**)&e->hObsStage, sizeof(double) * (size_t)nN));
     e->leafStageCap = (size_t)nN;
   }
   if ((int)e->leafVer.size() != nN) e->leafVer.assign(nN, 0);
-  LeafConst* lc = e->hLeafStage;
-  if (e->model == DCSMC_MODEL_MULTILEVEL)
-    for (int n = lo; n < hi; ++n) leafConstFor(e, n, lc[n]);
-  else
-    memset(lc + lo, 0, sizeof(LeafConst) * (size_t)(hi - lo));
   for (int n = lo; n < hi; ++n) e->leafVer[n] = e->leafVersion;
-  if (getenv("DCSMC_HOSTPROF")) fprintf(stderr, "[dcsmc hostprof] leaf entries [%d, %d) uploaded (version %llu)\n", lo, hi, (unsigned long long)e->leafVersion);
-  CK(cudaMemcpyAsync(e->dLeaf + lo, lc + lo, sizeof(LeafConst) * (size_t)(hi - lo), cudaMemcpyHostToDevice, e->stream));
-  e->pendingH2D += (int64_t)(sizeof(LeafConst) * (size_t)(hi - lo));
+  // binomial leaves carry a LeafConst (Cheng's constants, logBinomial); an observed leaf is one double. Ranges without
+  // binomial leaves (BASELINE config 4: 65 536 observed leaves) move 8 bytes per node instead of 104.
+  const bool multilevel = e->model == DCSMC_MODEL_MULTILEVEL;
+  const bool anyBinom = multilevel && (int)e->binomPrefix.size() == nN + 1 && e->binomPrefix[hi] > e->binomPrefix[lo];
+  const bool anyObs = multilevel && !e->leafObs.empty();
+  if (anyBinom || !multilevel) {
+    LeafConst* lc = e->hLeafStage;
+    if (multilevel)
+      for (int n = lo; n < hi; ++n) leafConstFor(e, n, lc[n]);
+    else
+      memset(lc + lo, 0, sizeof(LeafConst) * (size_t)(hi - lo));
+    CK(cudaMemcpyAsync(e->dLeaf + lo, lc + lo, sizeof(LeafConst) * (size_t)(hi - lo), cudaMemcpyHostToDevice, e->stream));
+    e->pendingH2D += (int64_t)(sizeof(LeafConst) * (size_t)(hi - lo));
+  }
+  if (anyObs) {
+    memcpy(e->hObsStage + lo, e->leafObs.data() + lo, sizeof(double) * (size_t)(hi - lo));
+    CK(cudaMemcpyAsync(e->dLeafObs + lo, e->hObsStage + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyHostToDevice, e->stream));
+    e->pendingH2D += (int64_t)(sizeof(double) * (size_t)(hi - lo));
+  }
+  if (getenv("DCSMC_HOSTPROF"))
+    fprintf(stderr, "[dcsmc hostprof] leaf entries [%d, %d) uploaded (version %llu, LeafConst %d, observations %d)\n", lo, hi,
+            (unsigned long long)e->leafVersion, (int)(anyBinom || !multilevel), (int)anyObs);
   return DCSMC_OK;
 }
 int uploadLeafTable(dcsmc_engine* e) {
@@ -568,7 +593,14 @@ int uploadTables(dcsmc_engine* e) {
     CK(re((void**)&e->dSumm, sizeof(NodeSummary) * nN));
     CK(cudaMemsetAsync(e->dSumm, 0, sizeof(NodeSummary) * nN, e->stream));
   }
-  CK(re((void**)&e->dLeaf, sizeof(LeafConst) * nN));
+  if (!(keep && e->dLeaf)) {  // entries of nodes that are not binomial leaves are never uploaded: keep them defined
+    CK(re((void**)&e->dLeaf, sizeof(LeafConst) * nN));
+    CK(cudaMemsetAsync(e->dLeaf, 0, sizeof(LeafConst) * nN, e->stream));
+  }
+  if (!(keep && e->dLeafObs)) {  // never read for a node that is not an observed leaf; zeros keep every byte defined
+    CK(re((void**)&e->dLeafObs, sizeof(double) * nN));
+    CK(cudaMemsetAsync(e->dLeafObs, 0, sizeof(double) * nN, e->stream));
+  }
   CK(re((void**)&e->dChildren, sizeof(int32_t) * std::max<size_t>(1, e->children.size())));
   CK(re((void**)&e->dInj, sizeof(double*) * nN));
   CK(re((void**)&e->dJavaState, sizeof(uint64_t) * nN));
@@ -849,8 +881,10 @@ cudaEvent_t nextEvent(dcsmc_engine* e) {
 
 // look-back descriptor words per node of a step (scan: A and B limbs; expansion: one)
 size_t descWordsPerNode(int N) {
+  // an even count keeps every node's first descriptor pair 16-byte aligned (k_scan2 moves a pair at a time)
+  static_assert(SCAN2_TILE == SCAN_TILE, "k_scan and k_scan2 share the descriptor budget");
   const size_t tilesS = (N + SCAN_TILE - 1) / SCAN_TILE, tilesE = (N + EXPAND_TILE - 1) / EXPAND_TILE;
-  return std::max(2 * tilesS, tilesE);
+  return (std::max(2 * tilesS, tilesE) + 1) / 2 * 2;
 }
 constexpr int MAX_CHUNKS = 16;
 
@@ -967,14 +1001,21 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
       CK(cudaMemsetAsync(offspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), sP));
     }
     const int mode = !leafFused ? 0 : (e->opt.resamplingScheme == DCSMC_STRATIFIED ? 1 : 2);
-    const size_t leafSmem = LEAF_WARPS * leaf_warp_smem_bytes(CH);
-    if (leafSmem > e->leafSmemSet[RNG]) {  // > 48 KB of dynamic shared memory needs the opt-in
-      CK(cudaFuncSetAttribute(k_leaf_propose<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leafSmem));
-      e->leafSmemSet[RNG] = leafSmem;
+    const bool v2 = e->leafVariant == 2;
+    const size_t leafSmem = LEAF_WARPS * (v2 ? leaf2_warp_smem_bytes(CH) : leaf_warp_smem_bytes(CH));
+    size_t& smemSet = v2 ? e->leaf2SmemSet[RNG] : e->leafSmemSet[RNG];
+    if (leafSmem > smemSet) {  // > 48 KB of dynamic shared memory needs the opt-in
+      if (v2)
+        CK(cudaFuncSetAttribute(k_leaf_propose2<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leafSmem));
+      else
+        CK(cudaFuncSetAttribute(k_leaf_propose<RNG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leafSmem));
+      smemSet = leafSmem;
     }
     ProfScope p(e, DCSMC_K_LEAF, sP);
-    k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS,
-                          leafSmem, sP>>>(c, blocksPerNode, CH, mode);
+    if (v2)
+      k_leaf_propose2<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS, leafSmem, sP>>>(c, blocksPerNode, CH, mode);
+    else
+      k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS, leafSmem, sP>>>(c, blocksPerNode, CH, mode);
   } else if (fusedSmall) {
     // the population fits in shared memory and the children's descriptors too: one block per node does the whole
     // node step (k_node_fused), the log weights never leave the SM
@@ -1006,8 +1047,20 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     int maxC = 0;
     for (int k = 0; k < st.count; ++k) maxC = std::max(maxC, nChildrenOf(e, e->planStepNodes[st.offset + k]));
     const bool wide = (double)maxC * std::log10((double)N) > 300.0;
+    // the level above the leaves: every child of every node is a binomial leaf in its native layout, and leaves
+    // always resample here (rESS == 1 < threshold), so nothing arrives weighted: k_internal_propose_lk
+    bool leafKids = e->leafKidsKernel && !wide && 1.0 < e->opt.relativeEssThreshold;
+    for (int k = 0; k < st.count && leafKids; ++k) {
+      const int n = e->planStepNodes[st.offset + k];
+      for (int cc = e->childOffsets[n]; cc < e->childOffsets[n + 1] && leafKids; ++cc) {
+        const int ch = e->children[cc];
+        leafKids = nodeKind(e, ch) == KIND_LEAF_BINOMIAL && !(!e->imported.empty() && e->imported[ch] == 1);
+      }
+    }
     ProfScope p(e, DCSMC_K_INTERNAL, sP);
-    if (wide)
+    if (leafKids)
+      k_internal_propose_lk<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+    else if (wide)
       k_internal_propose<RNG, true><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
     else
       k_internal_propose<RNG, false><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
@@ -1051,12 +1104,16 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     k_scan_java<<<st.count, 32, 0, sR>>>(c);
   } else {
     if (!st.leaf) {
-      const size_t needDesc = (size_t)st.count * tilesS;
+      const int tilesV = e->scanVariant == 1 ? tilesS : (N + SCAN2_TILE - 1) / SCAN2_TILE;
+      const size_t needDesc = (size_t)st.count * tilesV;
       c.descA = desc;
-      c.descB = desc + needDesc;
+      c.descB = desc + needDesc;  // k_scan only; k_scan2 keeps the (A, B) words of a tile next to each other
       CK(cudaMemsetAsync(desc, 0, 2 * needDesc * sizeof(unsigned long long), sR));
       ProfScope p(e, DCSMC_K_SCAN, sR);
-      k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, sR>>>(c, tilesS);
+      if (e->scanVariant == 1)
+        k_scan<<<(unsigned)(st.count * tilesS), SCAN_THREADS, 0, sR>>>(c, tilesS);
+      else
+        k_scan2<<<(unsigned)(st.count * tilesV), SCAN_THREADS, 0, sR>>>(c, tilesV);
     }
     ProfScope p(e, DCSMC_K_FINALIZE, sR);
     k_finalize<<<(st.count + 127) / 128, 128, 0, sR>>>(c);
@@ -1131,6 +1188,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.nodes = e->dNodes;
   c.stats = e->dStats;
   c.leaf = e->dLeaf;
+  c.leafObs = e->dLeafObs;
   c.children = e->dChildren;
   c.N = N;
   c.Npad = e->Npad;
@@ -1280,32 +1338,40 @@ int executePlan(dcsmc_engine* e, Plan& plan, CachedPlan* cached = nullptr) {
     CK(grow((void**)&e->dSumScratch, e->sumScratchCap, std::max<size_t>(1, total * (size_t)e->Npad), sizeof(double)));
   }
   bool descriptorsOnDevice = cached != nullptr && cached->onDevice;
+  if (plan.exportOrder.size() != plan.stepNodes.size()) {
+    plan.exportOrder = plan.stepNodes;
+    std::sort(plan.exportOrder.begin(), plan.exportOrder.end());
+  }
   {
+    // device list: [plan order | export order]
     int32_t* buf;
     if (cached) {
       if (cached->dStepNodes == nullptr) {
-        CK(cudaMalloc((void**)&cached->dStepNodes, std::max<size_t>(1, plan.stepNodes.size()) * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&cached->dStepNodes, std::max<size_t>(1, 2 * plan.stepNodes.size()) * sizeof(int32_t)));
         descriptorsOnDevice = false;
       }
       buf = cached->dStepNodes;
     } else {
-      if (plan.stepNodes.size() > e->stepNodesTmpCap) {
+      if (2 * plan.stepNodes.size() > e->stepNodesTmpCap) {
         if (e->dStepNodesTmp) {
           CK(cudaStreamSynchronize(e->stream));  // deferred calls may still read the old list
           cudaFree(e->dStepNodesTmp);
         }
         e->dStepNodesTmp = nullptr;
-        CK(cudaMalloc((void**)&e->dStepNodesTmp, plan.stepNodes.size() * sizeof(int32_t)));
-        e->stepNodesTmpCap = plan.stepNodes.size();
+        CK(cudaMalloc((void**)&e->dStepNodesTmp, 2 * plan.stepNodes.size() * sizeof(int32_t)));
+        e->stepNodesTmpCap = 2 * plan.stepNodes.size();
       } else if (e->deferred && e->inFlight) {
         CK(cudaStreamSynchronize(e->stream));  // the one temporary list is about to be overwritten
       }
       buf = e->dStepNodesTmp;
     }
     e->curStepNodes = buf;
-    if (!descriptorsOnDevice)
+    if (!descriptorsOnDevice) {
       CK(cudaMemcpyAsync(buf, plan.stepNodes.data(), plan.stepNodes.size() * sizeof(int32_t),
                          cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(buf + plan.stepNodes.size(), plan.exportOrder.data(), plan.exportOrder.size() * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, e->stream));
+    }
   }
   if (!descriptorsOnDevice) {
     // node descriptors for every node touched by the plan (a few nodes: one small copy each;
@@ -1452,7 +1518,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, CachedPlan* cached = nullptr) {
     e->exportCap = want;
   }
   if (nPlan > 0) {
-    k_export_stats<<<(unsigned)((nPlan + 255) / 256), 256, 0, e->stream>>>(e->dStats, e->curStepNodes, (int)nPlan, e->dExport + off,
+    k_export_stats<<<(unsigned)((nPlan + 255) / 256), 256, 0, e->stream>>>(e->dStats, e->curStepNodes + nPlan, (int)nPlan, e->dExport + off,
                                                                                e->dNodes, e->pool, (int32_t)e->poolGeneration);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->hExport + off, e->dExport + off, nPlan * sizeof(NodeStatsOut), cudaMemcpyDeviceToHost, e->stream));
@@ -1462,7 +1528,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, CachedPlan* cached = nullptr) {
   if (e->deferred) {
     // no host synchronisation: the caller keeps enqueueing (the next level, a collective, the closing barrier)
     e->inFlight = true;
-    e->pendNodes.insert(e->pendNodes.end(), plan.stepNodes.begin(), plan.stepNodes.end());
+    e->pendNodes.insert(e->pendNodes.end(), plan.exportOrder.begin(), plan.exportOrder.end());
     e->info.kernelLaunches += before.kernelLaunches;
     e->info.particleUpdates += before.particleUpdates;
     e->info.nodesProcessed += before.nodesProcessed;
@@ -1480,7 +1546,7 @@ int executePlan(dcsmc_engine* e, Plan& plan, CachedPlan* cached = nullptr) {
   e->info.deviceMs = ms;
   // the records stay in the pinned staging buffer; they are scattered into the per-node host tables when somebody
   // asks (flushStats) — a loop of back-to-back runs on a 131 071-node tree spent 2 ms per run in that scatter
-  e->pendNodes.insert(e->pendNodes.end(), plan.stepNodes.begin(), plan.stepNodes.end());
+  e->pendNodes.insert(e->pendNodes.end(), plan.exportOrder.begin(), plan.exportOrder.end());
   if (e->profile) {
     // per level batch: the device time of its launches, shared equally by the sibling nodes that ran in it
     // (what DefaultProcessorFactory reports as iterationProposalTime, DefaultProcessorFactory.java:41-50)
@@ -1510,11 +1576,15 @@ int executePlan(dcsmc_engine* e, Plan& plan, CachedPlan* cached = nullptr) {
 int prepare(dcsmc_engine* e) {
   int rc;
   if ((rc = ensureDevice(e))) return rc;
+  CKPOINT("prepare entry");
   if ((rc = validateForRun(e))) return rc;
   e->Npad = (int)alignUp((size_t)e->opt.nParticles, 32);
   if ((rc = uploadTables(e))) return rc;
+  CKPOINT("table upload");
   if ((rc = uploadInjected(e))) return rc;
+  CKPOINT("injected uniforms");
   if ((rc = ensurePool(e))) return rc;
+  CKPOINT("population pool");
   return DCSMC_OK;
 }
 
@@ -1743,6 +1813,9 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   if (const char* v = getenv("DCSMC_GRAPHS")) e->useGraphs = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_FUSE_SMALL")) e->fuseSmall = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_PARTITION_DARTS")) e->partitionDarts = atoi(v) != 0;
+  if (const char* v = getenv("DCSMC_LEAF_V")) e->leafVariant = atoi(v) == 1 ? 1 : 2;
+  if (const char* v = getenv("DCSMC_LEAFKIDS")) e->leafKidsKernel = atoi(v) != 0;
+  if (const char* v = getenv("DCSMC_SCAN_V")) e->scanVariant = atoi(v) == 1 ? 1 : 2;
   e->fuseMinNodes = e->smCount;
   if (const char* v = getenv("DCSMC_FUSE_MIN_NODES")) e->fuseMinNodes = std::max(1, atoi(v));
   if (const char* v = getenv("DCSMC_OVERLAP_CHUNKS")) e->overlapChunks = std::max(1, atoi(v));
@@ -1798,7 +1871,7 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   chk("population staging (device)");
   if (e->dSumm) cudaFree(e->dSumm);
   if (e->dSumScratch) cudaFree(e->dSumScratch);
-  void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dChildren, e->dStepNodesTmp, e->dInj, e->dJavaState,
+  void* ptrs[] = {e->dNodes, e->dStats, e->dLeaf, e->dLeafObs, e->dChildren, e->dStepNodesTmp, e->dInj, e->dJavaState,
                   e->dMarkovT, e->dMarkovPrior, e->pool, e->dCdf, e->dDesc, e->dOffspring, e->dInvTable,
                   e->dDartBuf, e->dChunkBin, e->dSegTotal};
   for (void* p : ptrs)
@@ -1915,32 +1988,51 @@ int32_t dcsmc_set_multilevel_model(dcsmc_engine* e, const int32_t* leafKind, con
   if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree first");
   if (!(variancePrior > 0)) return e->fail(DCSMC_EINVAL, "variancePrior must be > 0");
   const int nN = e->nNodes;
-  const std::vector<int32_t> oldKind = e->leafKind;
   const bool sameFamily = e->model == DCSMC_MODEL_MULTILEVEL && e->rate == variancePrior && !e->tablesDirty;
-  e->leafKind.assign(nN, DCSMC_LEAF_BINOMIAL);
-  if (leafKind) e->leafKind.assign(leafKind, leafKind + nN);
-  e->nTrials.assign(nN, 0);
-  e->nSuccesses.assign(nN, 0);
-  e->leafObs.assign(nN, 0.0);
-  if (leafObs) e->leafObs.assign(leafObs, leafObs + nN);
+  // validate before any state changes (DivideConquerMCAlgorithm.logBinomialPr :595-596 throws on bad counts)
   for (int n = 0; n < nN; ++n) {
     if (e->childOffsets[n + 1] != e->childOffsets[n]) continue;
-    if (e->leafKind[n] == DCSMC_LEAF_BINOMIAL) {
+    const int32_t kind = leafKind ? leafKind[n] : DCSMC_LEAF_BINOMIAL;
+    if (kind == DCSMC_LEAF_BINOMIAL) {
       if (!nTrials || !nSuccesses) return e->fail(DCSMC_EINVAL, "binomial leaves need nTrials/nSuccesses");
-      // DivideConquerMCAlgorithm.logBinomialPr :595-596 throws on these
       if (nTrials[n] < 0 || nSuccesses[n] < 0 || nSuccesses[n] > nTrials[n])
         return e->fail(DCSMC_EINVAL, "leaf %d: invalid (nTrials=%d, nSuccesses=%d)", n, nTrials[n], nSuccesses[n]);
-      e->nTrials[n] = nTrials[n];
-      e->nSuccesses[n] = nSuccesses[n];
-    } else if (e->leafKind[n] != DCSMC_LEAF_GAUSS_OBS) {
-      return e->fail(DCSMC_EINVAL, "leaf %d: unknown leaf kind %d", n, e->leafKind[n]);
+    } else if (kind != DCSMC_LEAF_GAUSS_OBS) {
+      return e->fail(DCSMC_EINVAL, "leaf %d: unknown leaf kind %d", n, kind);
     }
   }
-  e->model = DCSMC_MODEL_MULTILEVEL;
-  e->rate = variancePrior;
   // the memory plan depends on the leaf KINDS only (observed leaves hold no population); new counts /
   // observations on the same kinds are new input data for the same plan
-  if (sameFamily && oldKind == e->leafKind)
+  bool sameKinds = (int)e->leafKind.size() == nN;
+  if (sameKinds) {
+    if (leafKind)
+      sameKinds = memcmp(e->leafKind.data(), leafKind, sizeof(int32_t) * (size_t)nN) == 0;
+    else
+      for (int n = 0; n < nN && sameKinds; ++n) sameKinds = e->leafKind[n] == DCSMC_LEAF_BINOMIAL;
+  }
+  if (!sameKinds) {
+    if (leafKind)
+      e->leafKind.assign(leafKind, leafKind + nN);
+    else
+      e->leafKind.assign(nN, DCSMC_LEAF_BINOMIAL);
+  }
+  e->nTrials.resize(nN);
+  e->nSuccesses.resize(nN);
+  e->binomPrefix.resize((size_t)nN + 1);
+  e->binomPrefix[0] = 0;
+  for (int n = 0; n < nN; ++n) {  // counts of internal nodes and observed leaves are kept at 0 whatever the caller sent
+    const bool binom = e->childOffsets[n + 1] == e->childOffsets[n] && e->leafKind[n] == DCSMC_LEAF_BINOMIAL;
+    e->nTrials[n] = binom ? nTrials[n] : 0;
+    e->nSuccesses[n] = binom ? nSuccesses[n] : 0;
+    e->binomPrefix[n + 1] = e->binomPrefix[n] + (binom ? 1 : 0);
+  }
+  if (leafObs)
+    e->leafObs.assign(leafObs, leafObs + nN);
+  else
+    e->leafObs.assign(nN, 0.0);
+  e->model = DCSMC_MODEL_MULTILEVEL;
+  e->rate = variancePrior;
+  if (sameFamily && sameKinds)
     e->leafVersion++;
   else
     e->tablesDirty = true;
@@ -2033,6 +2125,26 @@ int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out) {
     return DCSMC_OK;
   }
   memcpy(out, e->hStats.data(), sizeof(dcsmc_node_stats_t) * e->nNodes);
+  return DCSMC_OK;
+}
+
+int32_t dcsmc_all_node_stats_columns(const dcsmc_engine* e, double* ess, double* relEss, double* logNormEstimate,
+                                     double* logScaling, int32_t* resampled, int32_t* done) {
+  if (!e) return DCSMC_EINVAL;
+  flushStats(e);
+  if (e->nNodes <= 0) return e->fail(DCSMC_ESTATE, "dcsmc_set_tree has not been called");
+  const size_t nN = (size_t)e->nNodes;
+  const bool have = e->hStats.size() == nN;  // else nothing was computed on this engine yet: done == 0 everywhere
+  const dcsmc_node_stats_t zero{};
+  for (size_t n = 0; n < nN; ++n) {
+    const dcsmc_node_stats_t& s = have ? e->hStats[n] : zero;
+    if (ess) ess[n] = s.ess;
+    if (relEss) relEss[n] = s.relEss;
+    if (logNormEstimate) logNormEstimate[n] = s.logNormEstimate;
+    if (logScaling) logScaling[n] = s.logScaling;
+    if (resampled) resampled[n] = s.resampled;
+    if (done) done[n] = s.done;
+  }
   return DCSMC_OK;
 }
 

@@ -160,12 +160,15 @@ class Engine:
         return v
 
     def all_node_stats(self) -> Dict[str, np.ndarray]:
-        arr = (F.NodeStats * self.nNodes)()
-        self._ck(self._L.dcsmc_all_node_stats(self._h, arr))
-        raw = np.frombuffer(arr, dtype=np.dtype([
-            ("ess", "f8"), ("relEss", "f8"), ("logNormEstimate", "f8"), ("logScaling", "f8"),
-            ("resampled", "i4"), ("done", "i4")]))
-        return {k: raw[k].copy() for k in raw.dtype.names}
+        # one array per field, filled by the library in one pass (no per-node struct walk or strided copy in Python)
+        n = self.nNodes
+        out = {k: np.empty(n) for k in ("ess", "relEss", "logNormEstimate", "logScaling")}
+        out["resampled"] = np.empty(n, np.int32)
+        out["done"] = np.empty(n, np.int32)
+        self._ck(self._L.dcsmc_all_node_stats_columns(
+            self._h, *[_ptr(out[k], C.c_double) for k in ("ess", "relEss", "logNormEstimate", "logScaling")],
+            _ptr(out["resampled"], C.c_int32), _ptr(out["done"], C.c_int32)))
+        return out
 
     def population(self, node: int, state=True, istate=False, weights=True, out=None):
         """Copy of the node's population after its node step. `out` = (state[6][N] f64, istate[N] i32,

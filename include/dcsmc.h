@@ -172,6 +172,11 @@ typedef struct dcsmc_node_stats_t {
 int32_t dcsmc_node_stats(const dcsmc_engine* e, int32_t node, dcsmc_node_stats_t* out);
 /* all nodes at once: out[nNodes] */
 int32_t dcsmc_all_node_stats(const dcsmc_engine* e, dcsmc_node_stats_t* out);
+/* the same table as one array per field (each [nNodes]; any pointer may be NULL): what a columnar consumer — the
+ * `timing` / `logZ` rows of DefaultProcessorFactory over a whole tree (DefaultProcessorFactory.java:41-54) — reads
+ * without a per-node struct walk */
+int32_t dcsmc_all_node_stats_columns(const dcsmc_engine* e, double* ess, double* relEss, double* logNormEstimate,
+                                     double* logScaling, int32_t* resampled, int32_t* done);
 
 /* Posterior summaries of impl-1 (printNodeStatistics / printDeltaNodeStatistics,
  * DivideConquerMCAlgorithm.java:433-507), computed on the device right after the node step of every
