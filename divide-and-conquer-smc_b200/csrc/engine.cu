@@ -493,7 +493,6 @@ int uploadLeafRange(dcsmc_engine* e, int lo, int hi) {
   const int nN = e->nNodes;
   if ((size_t)nN > e->leafStageCap) {
     if (e->hLeafStage) cudaFreeHost(e->hLeafStage);
-  if (e->hObsStage) cudaFreeHost(e->hObsStage);
     e->hLeafStage = nullptr;
     e->leafStageCap = 0;
     if (e->hObsStage) cudaFreeHost(e->hObsStage);
