@@ -178,6 +178,35 @@ def algorithmic_bytes(wl, N, multinomial, internal_only=False):
     return per, total
 
 
+# Bytes the kernels of a class must move IN THIS ENGINE'S LAYOUT (leaves are 2 columns + ancestors,
+# the resampled population is never materialised, observed leaves are constants), per step. The §8(d) split above
+# charges every child 40 + 100 B whatever it is; these are the compulsory bytes, so a fraction above 1 cannot occur.
+def layout_bytes(wl, N, multinomial, internal_only=False):
+    csr = wl["csr"]
+    off, ch = np.asarray(csr.childOffsets), np.asarray(csr.children)
+    nch = off[1:] - off[:-1]
+    is_leaf = nch == 0
+    nInt = int((~is_leaf).sum())
+    leaf_edges = int(is_leaf[ch].sum())  # edges into leaves
+    int_edges = len(ch) - leaf_edges     # edges into internal nodes
+    if internal_only:
+        # fused small-node kernel: children read through their ancestors (4 + 40 B), 48 B of state + 4 B ancestors
+        # written; log weights, CDF, darts and offspring counts stay in shared memory
+        return {"internal": N * (44 * int_edges + 52 * nInt)}
+    nLeaf = int(is_leaf.sum())
+    per = {
+        "leaf": N * nLeaf * (16 + 4),  # (mean, descObs) + offspring count (multinomial) or ancestor (stratified)
+        "internal": N * (20 * leaf_edges + 44 * int_edges + 56 * nInt),
+        "scan": N * nInt * 16,  # log weights in, CDF out (leaves: closed form, no scan)
+    }
+    if multinomial:
+        per["darts"] = N * nInt * 8  # grouped darts out
+        per["resample"] = N * (nInt * (8 + 8 + 4) + nLeaf * (4 + 4 + 4))  # CDF + darts in, ancestors out; leaves: counts zeroed, read, ancestors out
+    else:
+        per["resample"] = N * nInt * (8 + 4)
+    return per
+
+
 def make_ddc(cfg, wl, scheme, local):
     import dcsmc_b200 as d
 
@@ -248,6 +277,7 @@ def measure(name, cfg, args, D, sampler=None, detail=True):
     counted_nodes = wl["nInternal"] if internal_only else csr.nNodes
     updates_per_step = float(counted_nodes) * N
     per_bytes, alg_bytes_step = algorithmic_bytes(wl, N, multinomial, internal_only)
+    lay_bytes = layout_bytes(wl, N, multinomial, internal_only)
 
     for _ in range(args.warmup):
         ddc.run()
@@ -365,8 +395,15 @@ def measure(name, cfg, args, D, sampler=None, detail=True):
             "kernel_share_of_step": round(dom_ms / tot_ms, 4),
             "step": rec["step_roofline"],
             "by_kernel_ms": {k2: round(v["ms"], 3) for k2, v in prof.items() if v["launches"]},
-            "by_kernel_hbm_frac": {k2: round(per_bytes.get(k2, 0) * frac_of_tree / (v["ms"] * 1e-3) / 1e9 / peak, 4)
-                                   for k2, v in prof.items() if v["launches"] and v["ms"] > 0 and per_bytes.get(k2, 0)},
+            # fraction of the measured HBM peak per kernel class: bytes the class must move in this engine's layout
+            # (layout_bytes) / its time; "_8d" = the same with SURVEY §8(d)'s split, which charges 140 B per child
+            # whatever its footprint (a leaf child is 20 B here) and so can exceed 1
+            "frac_layout": round(lay_bytes.get(dom, 0) * frac_of_tree / (dom_ms * 1e-3) / 1e9 / peak, 4) if dom_ms > 0 else None,
+            "by_kernel_hbm_frac": {k2: round(lay_bytes.get(k2, 0) * frac_of_tree / (v["ms"] * 1e-3) / 1e9 / peak, 4)
+                                   for k2, v in prof.items() if v["launches"] and v["ms"] > 0 and lay_bytes.get(k2, 0)},
+            "by_kernel_hbm_frac_8d": {k2: round(per_bytes.get(k2, 0) * frac_of_tree / (v["ms"] * 1e-3) / 1e9 / peak, 4)
+                                      for k2, v in prof.items() if v["launches"] and v["ms"] > 0 and per_bytes.get(k2, 0)
+                                      and k2 in lay_bytes},
         }
         # the bound that actually applies to the two propose kernels: the fp64 pipe (2 warp instructions per clock
         # per SM: ncu sm__sass_thread_inst_executed_op_dfma_pred_on.avg.peak_sustained = 64 lanes/clk/SM).

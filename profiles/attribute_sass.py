@@ -30,8 +30,8 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 heads = [i for i, l in enumerate(raw) if l.startswith('"Kernel Name"')] + [len(raw)]
 rows = list(csv.reader(raw[heads[which]:heads[which + 1]]))
 hdr = rows[1]
-ia, ie, isrc = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Source")
-prof = [(int(r[ia], 16), r[isrc].strip(), int(r[ie])) for r in rows[2:] if len(r) > ie and r[ia].startswith("0x")]
+ia, ie, isrc, it = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("Thread Instructions Executed")
+prof = [(int(r[ia], 16), r[isrc].strip(), int(r[ie]), int(r[it])) for r in rows[2:] if len(r) > ie and r[ia].startswith("0x")]
 base = prof[0][0]
 byoff = {o: (s, c) for o, s, c in ins}
 
@@ -50,17 +50,19 @@ def region(f, ln):
                 name = n
         return name
     return f"{f}:{ln}"
-agg, fp64, tot = collections.Counter(), collections.Counter(), 0
-for a, s, c in prof:
+agg, fp64, thr, tot = collections.Counter(), collections.Counter(), collections.Counter(), 0
+for a, s, c, tc in prof:
     ch = byoff.get(a - base, (None, None))[1] or [("?", 0)]
     r = region(*ch[0])
     agg[r] += c
+    thr[r] += tc
     tot += c
     op = s.split()[1] if s.startswith("@") else s.split()[0]
     if op.startswith(("DMUL", "DADD", "DFMA", "DSETP", "MUFU")):
         fp64[r] += c
 print(f"kernel {fn}: {tot} warp instructions executed")
-print("| source region (innermost inlined function, or file:line) | share of executed warp instructions | of which fp64 |")
-print("|---|---|---|")
-for k, v in agg.most_common(14):
-    print(f"| {k} | {v / tot * 100:.1f} % | {fp64[k] / tot * 100:.1f} % |")
+print("| source region (innermost inlined function, or file:line) | share of executed warp instructions | of which fp64 | active lanes |")
+print("|---|---|---|---|")
+top = int(os.environ.get("ATTR_TOP", "14"))
+for k, v in agg.most_common(top):
+    print(f"| {k} | {v / tot * 100:.1f} % | {fp64[k] / tot * 100:.1f} % | {thr[k] / max(1, v):.1f} |")

@@ -23,11 +23,14 @@ for r in rows[1:]:
     name[k] = r[ix["Kernel Name"]]
     grid[k] = int(re.findall(r"\d+", r[ix["Grid Size"]])[0])
     per[k][r[ix["Metric Name"]]] += float(r[ix["Metric Value"]].replace(",", ""))
-CLASSES = {"leaf": r"k_leaf_propose", "internal": r"k_internal_propose", "scan": r"k_scan\b|k_scan\(", "darts": r"k_darts_count",
-           "expand": r"k_expand", "table": r"k_build_inverse_table", "fused": r"k_node_fused", "small": r"k_node_small"}
+CLASSES = {"leaf": r"k_leaf_propose", "internal": r"k_internal_propose", "scan": r"k_scan2?\b", "darts": r"k_darts_count|k_dart_partition",
+           "segres": r"k_seg_resample", "expand": r"k_expand", "table": r"k_build_inverse_table", "fused": r"k_node_fused",
+           "small": r"k_node_small"}
 # particles per launch: blocks of the propose kernels cover PROPOSE_THREADS = 256 particles of one node (leaf kernel: a block
 # covers LEAF_WARPS * CH particles); rather than decode every grid, count nodes from the tree: one run = 2800 leaves + 738 internal
-NODES = {"leaf": 2800, "internal": 738, "scan": 738, "darts": 738, "table": 738, "expand": 3538}
+NODES = {"leaf": 2800, "internal": 738, "scan": 738, "darts": 738, "table": 738, "segres": 738, "expand": 3538}
+if any(re.search(CLASSES["segres"], n) for n in name.values()):
+    NODES["expand"] = 2800  # partitioned resampling: k_expand only expands the leaves' offspring counts
 res = {"_source": f"{path} (ncu --metrics ..., cold-cache serialised launches), nParticles = {N}"}
 nRuns = None
 for cls, rx in CLASSES.items():
