@@ -217,7 +217,8 @@ struct dcsmc_engine {
   size_t offspringCap = 0;
   // partitioned multinomial resampling of large populations (k_dart_partition / k_seg_resample)
   bool partitionDarts = true;     // DCSMC_PARTITION_DARTS=0: k_darts_count + k_expand
-  int leafVariant = 2;            // DCSMC_LEAF_V=1: k_leaf_propose (r01) instead of k_leaf_propose2
+  int leafVariant = 3;            // DCSMC_LEAF_V=1: k_leaf_propose (r01), 2: k_leaf_propose2, 3: k_leaf_propose3
+  int leafChunkMax = 4096;        // DCSMC_LEAF_CH: particles a warp of k_leaf_propose3 works through before it drains
   bool leafKidsKernel = true;     // DCSMC_LEAFKIDS=0: the generic merge kernel also for the level above the leaves
   int scanVariant = 2;            // DCSMC_SCAN_V=1: k_scan (r01) instead of k_scan2
   double* dDartBuf = nullptr;
@@ -991,17 +992,28 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     ProfScope p(e, DCSMC_K_MARKOV, sP);
     k_markov_propose<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
   } else if (st.leaf) {
-    // each warp refills its lanes from a chunk of CH particles (see k_leaf_propose)
-    int CH = (N + LEAF_WARPS - 1) / LEAF_WARPS;
-    CH = std::min(512, std::max(32, (CH + 31) / 32 * 32));
-    const int blocksPerNode = (N + LEAF_WARPS * CH - 1) / (LEAF_WARPS * CH);
+    // each warp refills its lanes from a chunk of CH particles (see k_leaf_propose). k_leaf_propose / 2 buffer the
+    // chunk's candidates in shared memory (CH <= 512); k_leaf_propose3 does not: long chunks, the blocks of a node
+    // carrying equal shares
+    const int v = e->leafVariant;
+    int CH, blocksPerNode;
+    if (v == 3) {
+      blocksPerNode = (N + LEAF_WARPS * e->leafChunkMax - 1) / (LEAF_WARPS * e->leafChunkMax);
+      CH = (N + blocksPerNode * LEAF_WARPS - 1) / (blocksPerNode * LEAF_WARPS);
+      CH = std::max(32, (CH + 31) / 32 * 32);
+      blocksPerNode = (N + LEAF_WARPS * CH - 1) / (LEAF_WARPS * CH);
+    } else {
+      CH = (N + LEAF_WARPS - 1) / LEAF_WARPS;
+      CH = std::min(512, std::max(32, (CH + 31) / 32 * 32));
+      blocksPerNode = (N + LEAF_WARPS * CH - 1) / (LEAF_WARPS * CH);
+    }
     if (leafFused && e->opt.resamplingScheme == DCSMC_MULTINOMIAL) {
       c.offspring = offspring;
       CK(cudaMemsetAsync(offspring, 0, (size_t)st.count * c.Npad * sizeof(int32_t), sP));
     }
     const int mode = !leafFused ? 0 : (e->opt.resamplingScheme == DCSMC_STRATIFIED ? 1 : 2);
-    const bool v2 = e->leafVariant == 2;
-    const size_t leafSmem = LEAF_WARPS * (v2 ? leaf2_warp_smem_bytes(CH) : leaf_warp_smem_bytes(CH));
+    const bool v2 = v == 2;
+    const size_t leafSmem = v == 3 ? 0 : LEAF_WARPS * (v2 ? leaf2_warp_smem_bytes(CH) : leaf_warp_smem_bytes(CH));
     size_t& smemSet = v2 ? e->leaf2SmemSet[RNG] : e->leafSmemSet[RNG];
     if (leafSmem > smemSet) {  // > 48 KB of dynamic shared memory needs the opt-in
       if (v2)
@@ -1011,7 +1023,9 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
       smemSet = leafSmem;
     }
     ProfScope p(e, DCSMC_K_LEAF, sP);
-    if (v2)
+    if (v == 3)
+      k_leaf_propose3<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS, 0, sP>>>(c, blocksPerNode, CH, mode);
+    else if (v2)
       k_leaf_propose2<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS, leafSmem, sP>>>(c, blocksPerNode, CH, mode);
     else
       k_leaf_propose<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS, leafSmem, sP>>>(c, blocksPerNode, CH, mode);
@@ -1812,7 +1826,8 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   if (const char* v = getenv("DCSMC_GRAPHS")) e->useGraphs = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_FUSE_SMALL")) e->fuseSmall = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_PARTITION_DARTS")) e->partitionDarts = atoi(v) != 0;
-  if (const char* v = getenv("DCSMC_LEAF_V")) e->leafVariant = atoi(v) == 1 ? 1 : 2;
+  if (const char* v = getenv("DCSMC_LEAF_V")) e->leafVariant = std::min(3, std::max(1, atoi(v)));
+  if (const char* v = getenv("DCSMC_LEAF_CH")) e->leafChunkMax = std::min(65536, std::max(32, atoi(v) / 32 * 32));
   if (const char* v = getenv("DCSMC_LEAFKIDS")) e->leafKidsKernel = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_SCAN_V")) e->scanVariant = atoi(v) == 1 ? 1 : 2;
   e->fuseMinNodes = e->smCount;
