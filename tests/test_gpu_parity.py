@@ -303,3 +303,41 @@ def test_engine_matches_committed_golden_fixture():
                 assert dig(state) == case["state_sha256"][n], n
             rs, _, rw = e.population(0)
             assert dig(rs) == case["rootState_sha256"] and dig(rw) == case["rootWeights_sha256"]
+
+
+def ragged_school_rows(seed=11, counts=(1, 2, 3, 8, 9, 17, 40)):
+    """R -> school -> leaf with ragged leaf counts: one child (combine's C == 1 branch), exactly one and more than one
+    gather tile of k_internal_propose_lk2 (8 children), more than one tile of child descriptors (32)."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for s, c in enumerate(counts):
+        for l in range(c):
+            n = int(20 + rng.poisson(60))
+            rows.append(["R", f"s{s}", f"l{l}", str(n), str(int(rng.binomial(n, rng.beta(2, 2))))])
+    return rows
+
+
+@pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
+def test_kernel_variants_are_bit_identical_to_the_oracle(scheme, monkeypatch):
+    """Every selectable kernel variant (merge kernels for the level above the leaves incl. the shared-reciprocal fold
+    with its literal fallback forced for most / all folds, leaf kernels, scans, dart kernels) against the oracle."""
+    ds = d.MultiLevelDataset(rows=ragged_school_rows())
+    csr = ds.getTree().to_csr()
+    nT, nS = ds.leaf_arrays(csr)
+    N = 20011  # above the shared-memory node kernels, not a multiple of the block size
+    ref = o.run(csr, N, masterRandomSeed=5, resamplingScheme=scheme, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
+                elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
+    knobs = ("DCSMC_LEAFKIDS", "DCSMC_LK2_RANGE", "DCSMC_LEAF_V", "DCSMC_SCAN_V", "DCSMC_PARTITION_DARTS")
+    variants = [{}] + [{"DCSMC_LEAFKIDS": str(v)} for v in range(6)]
+    variants += [{"DCSMC_LEAFKIDS": "3", "DCSMC_LK2_RANGE": "1"}, {"DCSMC_LEAFKIDS": "4", "DCSMC_LK2_RANGE": "0"}]
+    variants += [{"DCSMC_LEAF_V": "1"}, {"DCSMC_LEAF_V": "2"}, {"DCSMC_SCAN_V": "1"}, {"DCSMC_PARTITION_DARTS": "0"}]
+    for env in variants:
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Engine(nParticles=N, masterRandomSeed=5, resamplingScheme=scheme, retainPopulations=1) as e:
+            e.set_tree(csr)
+            e.set_multilevel_model(nT, nS)
+            e.run()
+            compare_all(e, ref, csr)
