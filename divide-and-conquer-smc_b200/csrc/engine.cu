@@ -220,8 +220,9 @@ struct dcsmc_engine {
   int leafVariant = 3;            // DCSMC_LEAF_V=1: k_leaf_propose (r01), 2: k_leaf_propose2, 3: k_leaf_propose3
   int leafChunkMax = 4096;        // DCSMC_LEAF_CH: particles a warp of k_leaf_propose3 works through before it drains
   int leafKidsKernel = 1;         // DCSMC_LEAFKIDS=0: the generic merge kernel also for the level above the leaves;
-                                  // 1: k_internal_propose_lk; 2-5: k_internal_propose_lk2 (cp.async gathers;
-                                  // 3, 4: shared reciprocals; 4, 5: four blocks per SM)
+                                  // 1: k_internal_propose_lk; 2: the same with the shared-reciprocal fold
+                                  // (measured slower, kept as a tested experiment)
+  bool l2Prefetch = true;         // DCSMC_L2_PREFETCH=0: no prefetch hints in k_internal_propose
   int lk2Range = 100;             // DCSMC_LK2_RANGE (tests): see RunCtx::lkRange
   int scanVariant = 2;            // DCSMC_SCAN_V=1: k_scan (r01) instead of k_scan2
   double* dDartBuf = nullptr;
@@ -1075,15 +1076,9 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     }
     ProfScope p(e, DCSMC_K_INTERNAL, sP);
     if (leafKids && e->leafKidsKernel == 2)
-      k_internal_propose_lk2<RNG, false, 5><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
-    else if (leafKids && e->leafKidsKernel == 3)
-      k_internal_propose_lk2<RNG, true, 5><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
-    else if (leafKids && e->leafKidsKernel == 4)
-      k_internal_propose_lk2<RNG, true, 4><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
-    else if (leafKids && e->leafKidsKernel == 5)
-      k_internal_propose_lk2<RNG, false, 4><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+      k_internal_propose_lk<RNG, true><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
     else if (leafKids)
-      k_internal_propose_lk<RNG><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+      k_internal_propose_lk<RNG, false><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
     else if (wide)
       k_internal_propose<RNG, true><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
     else
@@ -1219,6 +1214,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.scheme = e->opt.resamplingScheme;
   c.maxAtt = e->opt.maxBetaAttempts;
   c.lkRange = e->lk2Range;
+  c.l2Prefetch = e->l2Prefetch && e->peers.empty() ? 1 : 0;
   c.nStates = e->nStates;
   c.javaStepsInternal = e->model == DCSMC_MODEL_MARKOV ? 1 : 2;
   c.seed = (uint64_t)e->opt.masterRandomSeed;
@@ -1840,7 +1836,8 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   if (const char* v = getenv("DCSMC_PARTITION_DARTS")) e->partitionDarts = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_LEAF_V")) e->leafVariant = std::min(3, std::max(1, atoi(v)));
   if (const char* v = getenv("DCSMC_LEAF_CH")) e->leafChunkMax = std::min(65536, std::max(32, atoi(v) / 32 * 32));
-  if (const char* v = getenv("DCSMC_LEAFKIDS")) e->leafKidsKernel = std::min(5, std::max(0, atoi(v)));
+  if (const char* v = getenv("DCSMC_LEAFKIDS")) e->leafKidsKernel = std::min(2, std::max(0, atoi(v)));
+  if (const char* v = getenv("DCSMC_L2_PREFETCH")) e->l2Prefetch = atoi(v) != 0;
   if (const char* v = getenv("DCSMC_LK2_RANGE")) e->lk2Range = std::min(100, std::max(0, atoi(v)));
   if (const char* v = getenv("DCSMC_SCAN_V")) e->scanVariant = atoi(v) == 1 ? 1 : 2;
   e->fuseMinNodes = e->smCount;

@@ -307,7 +307,7 @@ def test_engine_matches_committed_golden_fixture():
 
 def ragged_school_rows(seed=11, counts=(1, 2, 3, 8, 9, 17, 40)):
     """R -> school -> leaf with ragged leaf counts: one child (combine's C == 1 branch), exactly one and more than one
-    gather tile of k_internal_propose_lk2 (8 children), more than one tile of child descriptors (32)."""
+    small and large fan-outs, more than one tile of child descriptors (32)."""
     rng = np.random.default_rng(seed)
     rows = []
     for s, c in enumerate(counts):
@@ -328,8 +328,8 @@ def test_kernel_variants_are_bit_identical_to_the_oracle(scheme, monkeypatch):
     ref = o.run(csr, N, masterRandomSeed=5, resamplingScheme=scheme, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
                 elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
     knobs = ("DCSMC_LEAFKIDS", "DCSMC_LK2_RANGE", "DCSMC_LEAF_V", "DCSMC_SCAN_V", "DCSMC_PARTITION_DARTS")
-    variants = [{}] + [{"DCSMC_LEAFKIDS": str(v)} for v in range(6)]
-    variants += [{"DCSMC_LEAFKIDS": "3", "DCSMC_LK2_RANGE": "1"}, {"DCSMC_LEAFKIDS": "4", "DCSMC_LK2_RANGE": "0"}]
+    variants = [{}] + [{"DCSMC_LEAFKIDS": str(v)} for v in range(3)]
+    variants += [{"DCSMC_LEAFKIDS": "2", "DCSMC_LK2_RANGE": "1"}, {"DCSMC_LEAFKIDS": "2", "DCSMC_LK2_RANGE": "0"}]
     variants += [{"DCSMC_LEAF_V": "1"}, {"DCSMC_LEAF_V": "2"}, {"DCSMC_SCAN_V": "1"}, {"DCSMC_PARTITION_DARTS": "0"}]
     for env in variants:
         for k in knobs:
