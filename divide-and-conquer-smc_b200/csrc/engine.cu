@@ -222,7 +222,7 @@ struct dcsmc_engine {
   int leafKidsKernel = 1;         // DCSMC_LEAFKIDS=0: the generic merge kernel also for the level above the leaves;
                                   // 1: k_internal_propose_lk; 2: the same with the shared-reciprocal fold
                                   // (measured slower, kept as a tested experiment)
-  bool l2Prefetch = true;         // DCSMC_L2_PREFETCH=0: no prefetch hints in k_internal_propose
+  int l2Prefetch = 3;             // DCSMC_L2_PREFETCH: bit 0 prefetch hints in k_internal_propose, bit 1 in k_internal_propose_lk
   int lk2Range = 100;             // DCSMC_LK2_RANGE (tests): see RunCtx::lkRange
   int scanVariant = 2;            // DCSMC_SCAN_V=1: k_scan (r01) instead of k_scan2
   double* dDartBuf = nullptr;
@@ -1002,10 +1002,10 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     const int v = e->leafVariant;
     int CH, blocksPerNode;
     if (v == 3) {
-      blocksPerNode = (N + LEAF_WARPS * e->leafChunkMax - 1) / (LEAF_WARPS * e->leafChunkMax);
-      CH = (N + blocksPerNode * LEAF_WARPS - 1) / (blocksPerNode * LEAF_WARPS);
+      blocksPerNode = (N + LEAF3_WARPS * e->leafChunkMax - 1) / (LEAF3_WARPS * e->leafChunkMax);
+      CH = (N + blocksPerNode * LEAF3_WARPS - 1) / (blocksPerNode * LEAF3_WARPS);
       CH = std::max(32, (CH + 31) / 32 * 32);
-      blocksPerNode = (N + LEAF_WARPS * CH - 1) / (LEAF_WARPS * CH);
+      blocksPerNode = (N + LEAF3_WARPS * CH - 1) / (LEAF3_WARPS * CH);
     } else {
       CH = (N + LEAF_WARPS - 1) / LEAF_WARPS;
       CH = std::min(512, std::max(32, (CH + 31) / 32 * 32));
@@ -1028,7 +1028,7 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
     }
     ProfScope p(e, DCSMC_K_LEAF, sP);
     if (v == 3)
-      k_leaf_propose3<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS, 0, sP>>>(c, blocksPerNode, CH, mode);
+      k_leaf_propose3<RNG><<<(unsigned)(st.count * blocksPerNode), LEAF3_THREADS, 0, sP>>>(c, blocksPerNode, CH, mode);
     else if (v2)
       k_leaf_propose2<RNG><<<(unsigned)(st.count * blocksPerNode), PROPOSE_THREADS, leafSmem, sP>>>(c, blocksPerNode, CH, mode);
     else
@@ -1214,7 +1214,7 @@ int makeCtx(dcsmc_engine* e, RunCtx& c) {
   c.scheme = e->opt.resamplingScheme;
   c.maxAtt = e->opt.maxBetaAttempts;
   c.lkRange = e->lk2Range;
-  c.l2Prefetch = e->l2Prefetch && e->peers.empty() ? 1 : 0;
+  c.l2Prefetch = (e->l2Prefetch & 1 && e->peers.empty() ? 1 : 0) | (e->l2Prefetch & 2);
   c.nStates = e->nStates;
   c.javaStepsInternal = e->model == DCSMC_MODEL_MARKOV ? 1 : 2;
   c.seed = (uint64_t)e->opt.masterRandomSeed;
@@ -1837,7 +1837,7 @@ int32_t dcsmc_create(const dcsmc_options* opt, dcsmc_engine** out) {
   if (const char* v = getenv("DCSMC_LEAF_V")) e->leafVariant = std::min(3, std::max(1, atoi(v)));
   if (const char* v = getenv("DCSMC_LEAF_CH")) e->leafChunkMax = std::min(65536, std::max(32, atoi(v) / 32 * 32));
   if (const char* v = getenv("DCSMC_LEAFKIDS")) e->leafKidsKernel = std::min(2, std::max(0, atoi(v)));
-  if (const char* v = getenv("DCSMC_L2_PREFETCH")) e->l2Prefetch = atoi(v) != 0;
+  if (const char* v = getenv("DCSMC_L2_PREFETCH")) e->l2Prefetch = atoi(v) & 3;
   if (const char* v = getenv("DCSMC_LK2_RANGE")) e->lk2Range = std::min(100, std::max(0, atoi(v)));
   if (const char* v = getenv("DCSMC_SCAN_V")) e->scanVariant = atoi(v) == 1 ? 1 : 2;
   e->fuseMinNodes = e->smCount;
