@@ -19,6 +19,7 @@
 #include <memory>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dcsmc.h"
@@ -213,6 +214,7 @@ struct dcsmc_engine {
   std::map<std::string, char*> blobCache;
   char *dStage = nullptr, *hStage = nullptr;  // dcsmc_population_copy_to_host staging (device / pinned host)
   size_t stageCap = 0;
+  std::vector<cudaEvent_t> stageEvents;  // one per 4 MiB piece of a pipelined read-back
   int32_t* dOffspring = nullptr;  // multinomial: offspring counts
   size_t offspringCap = 0;
   // partitioned multinomial resampling of large populations (k_dart_partition / k_seg_resample)
@@ -1889,6 +1891,7 @@ int32_t dcsmc_destroy(dcsmc_engine* e) {
   if (e->evT0) cudaEventDestroy(e->evT0);
   if (e->evT1) cudaEventDestroy(e->evT1);
   chk("timer events");
+  for (cudaEvent_t ev : e->stageEvents) cudaEventDestroy(ev);
   if (e->hStage) cudaFreeHost(e->hStage);
   chk("population staging (host)");
   if (e->dStage) cudaFree(e->dStage);
@@ -2291,11 +2294,58 @@ int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* sta
   e->info.kernelLaunches++;
   k_materialise<<<(N + 255) / 256, 256, 0, e->stream>>>(c, node, dS, dI, dW, (size_t)N);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(e->hStage, e->dStage, total, cudaMemcpyDeviceToHost, e->stream));
+  // staging range [off, off + len) -> the caller's arrays (a range may straddle the three sections)
+  auto copyOut = [&](size_t off, size_t len) {
+    const struct { size_t at, bytes; char* dst; } sec[3] = {{0, bS, reinterpret_cast<char*>(state)},
+                                                            {oI, bI, reinterpret_cast<char*>(istate)},
+                                                            {oW, bW, reinterpret_cast<char*>(weights)}};
+    for (const auto& q : sec) {
+      if (!q.dst || q.bytes == 0) continue;
+      const size_t lo = std::max(off, q.at), hi = std::min(off + len, q.at + q.bytes);
+      if (lo < hi) memcpy(q.dst + (lo - q.at), e->hStage + lo, hi - lo);
+    }
+  };
+  constexpr size_t PIPE_CHUNK = 4u << 20;
+  if (total <= PIPE_CHUNK) {
+    CK(cudaMemcpyAsync(e->hStage, e->dStage, total, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    copyOut(0, total);
+    return DCSMC_OK;
+  }
+  // Large populations (cfg3's root: 56 MB): the device -> pinned copy is cut into 4 MiB pieces, each followed by an
+  // event, and up to four host threads move finished pieces into the caller's arrays while the next ones are still on
+  // the bus — the call costs max(PCIe, host memcpy) instead of their sum, and the host side is no longer one thread's
+  // memcpy (r02d: the end-to-end step of the bench spent more time here than in all the host-side planning).
+  const size_t nChunks = (total + PIPE_CHUNK - 1) / PIPE_CHUNK;
+  while (e->stageEvents.size() < nChunks) {
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->stageEvents.push_back(ev);
+  }
+  for (size_t k = 0; k < nChunks; ++k) {
+    const size_t off = k * PIPE_CHUNK, len = std::min(PIPE_CHUNK, total - off);
+    CK(cudaMemcpyAsync(e->hStage + off, e->dStage + off, len, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaEventRecord(e->stageEvents[k], e->stream));
+  }
+  const int nThreads = (int)std::min<size_t>(4, nChunks);
+  std::vector<cudaError_t> terr(nThreads, cudaSuccess);
+  auto worker = [&](int t) {
+    cudaSetDevice(e->opt.device);
+    for (size_t k = (size_t)t; k < nChunks; k += (size_t)nThreads) {
+      const cudaError_t r = cudaEventSynchronize(e->stageEvents[k]);
+      if (r != cudaSuccess) {
+        terr[t] = r;
+        return;
+      }
+      copyOut(k * PIPE_CHUNK, std::min(PIPE_CHUNK, total - k * PIPE_CHUNK));
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nThreads; ++t) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < nThreads; ++t) CK(terr[t]);
   CK(cudaStreamSynchronize(e->stream));
-  if (state) memcpy(state, e->hStage, bS);
-  if (istate) memcpy(istate, e->hStage + oI, bI);
-  if (weights) memcpy(weights, e->hStage + oW, bW);
   return DCSMC_OK;
 }
 
