@@ -327,10 +327,11 @@ def test_kernel_variants_are_bit_identical_to_the_oracle(scheme, monkeypatch):
     N = 20011  # above the shared-memory node kernels, not a multiple of the block size
     ref = o.run(csr, N, masterRandomSeed=5, resamplingScheme=scheme, rngMode=o.RNG_PHILOX, sumMode=o.SUM_EXACT,
                 elemMode=o.ELEM_FDLIBM, nTrials=nT, nSuccesses=nS, dump=True)
-    knobs = ("DCSMC_LEAFKIDS", "DCSMC_LK2_RANGE", "DCSMC_LEAF_V", "DCSMC_SCAN_V", "DCSMC_PARTITION_DARTS")
+    knobs = ("DCSMC_LEAFKIDS", "DCSMC_LK2_RANGE", "DCSMC_LEAF_V", "DCSMC_SCAN_V", "DCSMC_PARTITION_DARTS", "DCSMC_L2_PREFETCH")
     variants = [{}] + [{"DCSMC_LEAFKIDS": str(v)} for v in range(3)]
     variants += [{"DCSMC_LEAFKIDS": "2", "DCSMC_LK2_RANGE": "1"}, {"DCSMC_LEAFKIDS": "2", "DCSMC_LK2_RANGE": "0"}]
     variants += [{"DCSMC_LEAF_V": "1"}, {"DCSMC_LEAF_V": "2"}, {"DCSMC_SCAN_V": "1"}, {"DCSMC_PARTITION_DARTS": "0"}]
+    variants += [{"DCSMC_L2_PREFETCH": "0"}, {"DCSMC_L2_PREFETCH": "0", "DCSMC_LEAFKIDS": "0"}]
     for env in variants:
         for k in knobs:
             monkeypatch.delenv(k, raising=False)
