@@ -221,9 +221,8 @@ struct dcsmc_engine {
   bool partitionDarts = true;     // DCSMC_PARTITION_DARTS=0: k_darts_count + k_expand
   int leafVariant = 3;            // DCSMC_LEAF_V=1: k_leaf_propose (r01), 2: k_leaf_propose2, 3: k_leaf_propose3
   int leafChunkMax = 4096;        // DCSMC_LEAF_CH: particles a warp of k_leaf_propose3 works through before it drains
-  int leafKidsKernel = 1;         // DCSMC_LEAFKIDS=0: the generic merge kernel also for the level above the leaves;
-                                  // 1: k_internal_propose_lk; 2: the same with the shared-reciprocal fold
-                                  // (measured slower, kept as a tested experiment)
+  int leafKidsKernel = 2;         // DCSMC_LEAFKIDS=0: the generic merge kernel also for the level above the leaves;
+                                  // 1: k_internal_propose_lk with the literal fold; 2: with the shared-reciprocal fold
   int l2Prefetch = 3;             // DCSMC_L2_PREFETCH: bit 0 prefetch hints in k_internal_propose, bit 1 in k_internal_propose_lk
   int lk2Range = 100;             // DCSMC_LK2_RANGE (tests): see RunCtx::lkRange
   int scanVariant = 2;            // DCSMC_SCAN_V=1: k_scan (r01) instead of k_scan2
