@@ -1076,14 +1076,19 @@ int launchStep(dcsmc_engine* e, const RunCtx& base, const Step& st, const ChunkC
       }
     }
     ProfScope p(e, DCSMC_K_INTERNAL, sP);
+    // 2-D grid (x = tile, y = node; the kernels are told by tilesPerNode == 0) whenever the step's node count fits
+    // gridDim.y: spares every block the integer division of the flat index
+    const bool grid2d = st.count <= 65535;
+    const dim3 gridM = grid2d ? dim3((unsigned)tilesP, (unsigned)st.count) : dim3((unsigned)gridP);
+    const int tpn = grid2d ? 0 : tilesP;
     if (leafKids && e->leafKidsKernel == 2)
-      k_internal_propose_lk<RNG, true><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+      k_internal_propose_lk<RNG, true><<<gridM, PROPOSE_THREADS, 0, sP>>>(c, tpn);
     else if (leafKids)
-      k_internal_propose_lk<RNG, false><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+      k_internal_propose_lk<RNG, false><<<gridM, PROPOSE_THREADS, 0, sP>>>(c, tpn);
     else if (wide)
-      k_internal_propose<RNG, true><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+      k_internal_propose<RNG, true><<<gridM, PROPOSE_THREADS, 0, sP>>>(c, tpn);
     else
-      k_internal_propose<RNG, false><<<(unsigned)gridP, PROPOSE_THREADS, 0, sP>>>(c, tilesP);
+      k_internal_propose<RNG, false><<<gridM, PROPOSE_THREADS, 0, sP>>>(c, tpn);
   }
   if (sR != sP) {  // the chain of this chunk starts when its propose kernel is done
     cudaEvent_t ev = nextEvent(e);
@@ -2340,9 +2345,17 @@ int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* sta
     }
   };
   std::vector<std::thread> pool;
-  for (int t = 1; t < nThreads; ++t) pool.emplace_back(worker, t);
+  int started = 1;  // this thread is worker 0; a thread that cannot be created leaves its pieces to the sweep below
+  try {
+    for (int t = 1; t < nThreads; ++t) {
+      pool.emplace_back(worker, t);
+      ++started;
+    }
+  } catch (...) {
+  }
   worker(0);
   for (auto& th : pool) th.join();
+  for (int t = started; t < nThreads; ++t) worker(t);  // no exception may cross the C ABI
   for (int t = 0; t < nThreads; ++t) CK(terr[t]);
   CK(cudaStreamSynchronize(e->stream));
   return DCSMC_OK;
