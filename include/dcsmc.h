@@ -237,7 +237,9 @@ int32_t dcsmc_population_view(dcsmc_engine* e, int32_t node, dcsmc_population_vi
  * resampling ran) to host buffers; any pointer may be NULL.
  *   state   [6][N]: mean, msgVar, logLik, descObs, descVar, variance (multilevel model)
  *   istate  [N]   : Markov particle
- *   weights [N]   : getNormalizedWeight(i) */
+ *   weights [N]   : getNormalizedWeight(i)
+ * Blocking. Populations above 4 MiB are copied device -> pinned staging in 4 MiB pieces and moved into the caller's
+ * (pageable) arrays by up to four short-lived host threads while the next pieces are still on the bus. */
 int32_t dcsmc_population_copy_to_host(dcsmc_engine* e, int32_t node, double* state,
                                       int32_t* istate, double* weights);
 
