@@ -2418,7 +2418,7 @@ int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre, i
 
 int32_t dcsmc_debug_eval(dcsmc_engine* e, int32_t op, const double* x, double* y, int64_t n) {
   if (!e) return DCSMC_EINVAL;
-  if (!x || !y || n < 0 || op < 0 || (op & 0xff) > 2) return e->fail(DCSMC_EINVAL, "dcsmc_debug_eval: bad arguments");
+  if (!x || !y || n < 0 || op < 0 || (op & 0xff) > 6) return e->fail(DCSMC_EINVAL, "dcsmc_debug_eval: bad arguments");
   if (n == 0) return DCSMC_OK;
   CK(cudaSetDevice(e->opt.device));
   double *dx = nullptr, *dy = nullptr;

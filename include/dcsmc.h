@@ -249,7 +249,9 @@ int32_t dcsmc_debug_copy_node(dcsmc_engine* e, int32_t node, double* statePre,
                               int32_t* istatePre, double* logWeights, int32_t* ancestors);
 
 /* Parity/debug: evaluate an elementary function of the numerics contract on the DEVICE for n host
- * inputs (op 0: log, 1: exp — the fdlibm algorithms StrictMath specifies). */
+ * inputs (op 0: log, 1: exp — the fdlibm algorithms StrictMath specifies; 2 | node << 8: Philox uniforms;
+ * 3: the kernels' two straight-line division forms on the pairs (x[2k], x[2k+1]) -> (y[2k], y[2k+1]), which must equal
+ * IEEE x[2k] / x[2k+1]; 4, 5: the straight-line log / exp of the leaf kernels, valid for non-rare arguments). */
 int32_t dcsmc_debug_eval(dcsmc_engine* e, int32_t op, const double* x, double* y, int64_t n);
 /* The same functions from the same header compiled for the host (no device needed): op 0 log, 1 exp,
  * 2 | node << 8: Philox uniform number (uint64)x[i] of `node`, seed 31. */

@@ -200,6 +200,53 @@ def test_device_elementary_functions_equal_fdlibm_oracle():
         assert np.array_equal(ud, uo)
 
 
+def test_straight_line_divisions_and_elementary_functions_are_ieee_exact():
+    """The hot kernels do not use nvcc's '/' everywhere: a quotient over a shared refined reciprocal (div_by /
+    rcp_refined, the merge kernels' folds) and dc_div_safe (the leaf kernels' fdlibm) run the compiler's fast-path
+    sequence without its range checks. Inside the operand range the kernels guarantee, both must return the correctly
+    rounded IEEE quotient — checked here against numpy's division bit for bit on random and adversarial operands
+    (mantissas of all ones / one ulp off a power of two, equal operands, operands 2^+-200 apart). Likewise the
+    straight-line log / exp equal the general routines on every non-rare argument."""
+    rng = np.random.default_rng(11)
+    n = 400000
+
+    def rand_operands(k, emin, emax):
+        mant = rng.integers(0, 1 << 52, k, dtype=np.uint64)
+        expo = rng.integers(1023 + emin, 1023 + emax, k, dtype=np.uint64)
+        sign = rng.integers(0, 2, k, dtype=np.uint64) << np.uint64(63)
+        return (sign | (expo << np.uint64(52)) | mant).view(np.float64)
+
+    a = rand_operands(n, -200, 200)
+    b = rand_operands(n, -200, 200)
+    edge = np.array([1.0, np.nextafter(1.0, 2.0), np.nextafter(1.0, 0.0), np.nextafter(2.0, 0.0), 3.0, 1.0 / 3.0, 1e-60, 1e60,
+                     0.1, 7.0, np.nextafter(4.0, 0.0), 1.5])
+    ea, eb = np.meshgrid(edge, edge)
+    a = np.concatenate([a, ea.ravel(), -ea.ravel(), np.zeros(8)])
+    b = np.concatenate([b, eb.ravel(), eb.ravel(), edge[:8]])
+    # the exact ties of the final correction step: power-of-two dividends over divisors whose mantissa is all ones
+    # (1 / (1 - 2^-53) must round to 1 + 2^-52); the reciprocal seed's low word = 1, as in nvcc's own expansion, decides them
+    ones = (np.uint64(0x000FFFFFFFFFFFFF) | (rng.integers(1023 - 150, 1023 + 150, 4000, dtype=np.uint64) << np.uint64(52))).view(np.float64)
+    pow2 = np.ldexp(1.0, rng.integers(-150, 150, 4000)) * rng.choice([-1.0, 1.0], 4000)
+    a = np.concatenate([a, pow2, rand_operands(4000, -150, 150), ones])
+    b = np.concatenate([b, ones, ones, np.abs(pow2)])
+    x = np.empty(2 * len(a))
+    x[0::2], x[1::2] = a, b
+    with Engine(nParticles=8) as e:
+        y = e.debug_eval(3, x)
+        want = a / b
+        assert np.array_equal(y[0::2], want), "quotient over a shared refined reciprocal"
+        assert np.array_equal(y[1::2], want), "dc_div_safe"
+        # straight-line log / exp against the general routines (arguments away from the rare sets: |x - 1| >= 2^-20,
+        # normal range; 2^-28 <= |x| < 708)
+        xs = np.concatenate([np.exp(rng.uniform(-700, 700, 200000)), rng.uniform(1e-12, 0.999, 200000), rng.uniform(1.001, 50, 100000)])
+        hm = (xs.view(np.uint64) >> np.uint64(32)).astype(np.int64) & 0xFFFFF  # dc_log_is_rare's mantissa test
+        xs = xs[((hm + 2) & 0xFFFFF) >= 3]
+        assert np.array_equal(e.debug_eval(4, xs), e.debug_eval(0, xs))
+        xe = np.concatenate([rng.uniform(-707, 707, 200000), rng.uniform(-3, 3, 200000)])
+        xe = xe[np.abs(xe) >= 2.0 ** -28]
+        assert np.array_equal(e.debug_eval(5, xe), e.debug_eval(1, xe))
+
+
 @pytest.mark.parametrize("scheme", [o.MULTINOMIAL, o.STRATIFIED])
 @pytest.mark.parametrize("threshold", [1.0 + 1e-10, 0.5])
 def test_java_order_sums_bit_exact_against_java_order_oracle(scheme, threshold):
